@@ -1,0 +1,138 @@
+/*
+ * nn_b200.h -- C ABI of the B200-native brute-force 1-nearest-neighbour path.
+ *
+ * Drop-in boundary for wu-kan/multicore-hw2's hot path.  Every entry point names the
+ * reference interface it replaces (files under /root/reference/sources/src/).
+ *
+ * Conventions: plain pointers and sizes only, no C++/torch types.  Points are AoS float32,
+ * queries S = [m][k], references R = [n][k], exactly as the reference's harness passes them
+ * (generator.h:32-50).  Results are 0-based indices into R; ties go to the lowest index and the
+ * distance arithmetic is v0's (core.cu:44-54): IEEE round-to-nearest sub/mul/add, no FMA,
+ * summed over the dimensions in order -- results are bit-identical to v0::cudaCallback.
+ * 3 <= k <= 16.  Functions returning int return NN_B200_OK (0) or a negative NN_B200_E* code;
+ * nn_b200_last_error() gives the message.  There is NO CPU fallback: without a usable CUDA
+ * device every compute entry fails (the reference falls back to v0, core.cu:869-870).
+ */
+#ifndef NN_B200_H
+#define NN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define NN_B200_API __attribute__((visibility("default")))
+#else
+#define NN_B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NN_B200_OK 0
+#define NN_B200_EINVAL (-1)  /* bad k/m/n, null or misaligned pointer */
+#define NN_B200_ECUDA (-2)   /* a CUDA runtime call or kernel launch failed */
+#define NN_B200_ENCCL (-3)   /* NCCL could not be loaded / initialised / failed */
+#define NN_B200_ENODEV (-4)  /* no CUDA device visible */
+
+#define NN_B200_KMIN 3
+#define NN_B200_KMAX 16
+
+/* v0's start state (INFINITY, index 0), core.cu:39-40, as a packed key. */
+#define NN_B200_KEY_INIT 0x7F80000000000000ull
+
+/* ------------------------------------------------------------------------------------------
+ * 1. The reference's entry point, host pointers in, malloc'ed indices out.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces the global `cudaCallback` (core.h:71, core.cu:1282-1297) and therefore
+ * `v8::cudaCallback` (core.cu:856-958) which it forwards to.  Same contract: S and R are host
+ * arrays owned by the caller and only read; *results is allocated with malloc(sizeof(int)*m)
+ * and freed by the caller (core.cu:935; main.cu:98).  Synchronous.  Uses every visible GPU
+ * (at most n, core.cu:867-868; NN_B200_GPUS=<count> caps it), sharding R contiguously
+ * (core.cu:875-883) and merging per-query packed keys with ncclAllReduce(min, u64) instead of
+ * the reference's host-side second-level reduce (core.cu:936-957).  On failure it prints
+ * "Error: ..." and exit(1)s like the reference's CHECK macro (core.h:77-87).
+ * The library ALSO exports the C++ symbol `::cudaCallback(int,int,int,float*,float*,int**)`
+ * (_Z12cudaCallbackiiiPfS_PPi) with the same body, so the reference's unmodified main.cu links. */
+NN_B200_API void nn_b200_cudaCallback(int k, int m, int n, float *searchPoints, float *referencePoints,
+                          int **results);
+
+/* Same work, caller-provided result buffer (m ints, host) and an error code instead of exit(1).
+ * num_gpus <= 0 means "all visible" (subject to NN_B200_GPUS). */
+NN_B200_API int nn_b200_search_host(int k, int m, int n, const float *searchPoints,
+                        const float *referencePoints, int *results, int num_gpus);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Device-resident building blocks (what v7/v8 run between their H2D and D2H copies).
+ *    All pointers are DEVICE pointers on the current CUDA device; `stream` is a cudaStream_t
+ *    (NULL = default stream).  Calls are asynchronous with respect to the host.
+ * ------------------------------------------------------------------------------------------ */
+
+/* keys[i] = NN_B200_KEY_INIT for i < m: v0's per-query start state (core.cu:39-40). */
+NN_B200_API int nn_b200_keys_init(uint64_t *d_keys, int m, void *stream);
+
+/* Fused squared-distance + argmin of m queries against n references, folded into d_keys with a
+ * 64-bit atomicMin: keys[i] = min(keys[i], (float_bits(d2) << 32) | (index_base + j)).
+ * Replaces `cudaCallbackKernel<1024>` (core.cu:808-855 / 662-709), the transpose it depends on
+ * (`mat_inv_kernel`, core.cu:792-807 -- references are consumed in their native AoS layout) and
+ * the host second-level reduction (core.cu:765-787, 936-957).  `index_base` is the global index
+ * of d_R[0] (shard offset, core.cu:932-933).  Because the fold is a min, a reference set may be
+ * fed in any number of calls (chunks, shards) in any order.  d_R must be 16-byte aligned. */
+NN_B200_API int nn_b200_nearest_keys(int k, int m, int64_t n, const float *d_S, const float *d_R,
+                         uint32_t index_base, uint64_t *d_keys, void *stream);
+
+/* results[i] = (int)(keys[i] & 0xffffffff): the `result[...] = ind_s[0]` store of core.cu:853-854
+ * after the merge. */
+NN_B200_API int nn_b200_keys_unpack(const uint64_t *d_keys, int m, int *d_results, void *stream);
+
+/* AoS [n][k] -> SoA [k][n], out[kInd*n + nInd] = in[nInd*k + kInd].  Replaces `mat_inv_kernel`
+ * (core.cu:792-807; also 315-330, 533-548, 646-661) with a shared-memory staged repack whose
+ * global loads and stores are both 128-bit and fully coalesced. */
+NN_B200_API int nn_b200_repack_soa(int k, int64_t n, const float *d_in, float *d_out, void *stream);
+
+/* Same fused search over a reference set already repacked to SoA [k][n] (the layout v4/v7/v8
+ * search in, core.cu:830-835).  Same keys as nn_b200_nearest_keys. */
+NN_B200_API int nn_b200_nearest_keys_soa(int k, int m, int64_t n, const float *d_S, const float *d_R_soa,
+                             uint32_t index_base, uint64_t *d_keys, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Host-side helpers
+ * ------------------------------------------------------------------------------------------ */
+
+/* Contiguous reference shard of rank `shard` of `num_shards` (v8's partition, core.cu:875-883,
+ * without its duplicated-last-point hack: an empty shard is allowed).  Shard starts are
+ * multiples of 4 references so that every shard stays 16-byte aligned for any k. */
+NN_B200_API int nn_b200_shard_range(int64_t n, int num_shards, int shard, int64_t *begin, int64_t *count);
+
+/* Number of CUDA devices the host entry would use for n references (core.cu:865-868). */
+NN_B200_API int nn_b200_device_count(int64_t n);
+
+/* Kernels launched by this library in this process so far (bench.py's `gpu_launches`). */
+NN_B200_API int64_t nn_b200_launch_count(void);
+
+/* Message of the last error on the calling thread ("" if none). */
+NN_B200_API const char *nn_b200_last_error(void);
+
+/* Tuning knobs for benchmarking/sweeps; production code never needs them.  Known names:
+ * "variant" (0 auto, 1 query-register kernel, 2 reference-register kernel, 3 plain kernel),
+ * "splits" (0 auto), "h2d_chunk_bytes".  Returns NN_B200_EINVAL for an unknown name. */
+NN_B200_API int nn_b200_set_option(const char *name, int64_t value);
+
+/* Measurement aid: sustained rate, in lane-operations per second, at which this device issues
+ * NON-fused FP32 multiplies and adds (scalar FMUL/FADD when packed == 0, packed f32x2 FMUL2/FADD2
+ * otherwise) -- the measured denominator of the FP32 roofline.  Synchronous; ~`iters` * 64 ops per thread. */
+NN_B200_API int nn_b200_probe_fp32(int packed, int iters, double *lane_ops_per_s);
+
+/* Human-readable description of the launch plan nn_b200_nearest_keys would use (variant, tile,
+ * grid); written into buf (NUL-terminated, truncated to len). */
+NN_B200_API int nn_b200_describe_plan(int k, int m, int64_t n, char *buf, size_t len);
+
+#ifdef __cplusplus
+} /* extern "C" */
+
+/* The reference's own C++-linkage symbol (core.h:71). */
+NN_B200_API void cudaCallback(int k, int m, int n, float *searchPoints, float *referencePoints, int **results);
+#endif
+
+#endif /* NN_B200_H */

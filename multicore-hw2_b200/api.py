@@ -1,0 +1,99 @@
+"""Host-pointer API: the reference's ``cudaCallback`` and its helpers, through the C ABI."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+_libc = ctypes.CDLL(None)
+_libc.free.argtypes = [ctypes.c_void_p]
+
+
+def _host_f32(a, what: str) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+def cudaCallback(k: int, m: int, n: int, searchPoints, referencePoints) -> np.ndarray:
+    """``cudaCallback(k, m, n, searchPoints, referencePoints, &results)`` of the reference
+    (core.h:71; core.cu:1282-1297), through the exported C symbol ``nn_b200_cudaCallback``.
+
+    searchPoints is [m][k], referencePoints is [n][k] (host, float32, AoS).  Returns the int32[m]
+    nearest indices.  The C side malloc()s the result exactly like the reference (core.cu:935);
+    it is copied into a numpy array and freed here.  Failures terminate the process with the
+    reference's "Error: ..." message (CHECK macro, core.h:77-87); use :func:`search_host` for an
+    exception instead."""
+    S = _host_f32(searchPoints, "searchPoints")
+    R = _host_f32(referencePoints, "referencePoints")
+    if S.size != k * m or R.size != k * n:
+        raise ValueError(f"expected {k*m} query floats and {k*n} reference floats, got {S.size} and {R.size}")
+    res = ctypes.POINTER(ctypes.c_int)()
+    lib().nn_b200_cudaCallback(k, m, n, S.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                               R.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), ctypes.byref(res))
+    out = np.ctypeslib.as_array(res, shape=(max(m, 1),))[:m].copy() if m > 0 else np.empty(0, np.int32)
+    _libc.free(ctypes.cast(res, ctypes.c_void_p))
+    return out.astype(np.int32, copy=False)
+
+
+def search_host(searchPoints, referencePoints, k: int | None = None, num_gpus: int = 0, out=None) -> np.ndarray:
+    """Same search with an exception on failure.  Accepts numpy arrays or (pinned) torch CPU
+    tensors; the host buffers are handed to the C ABI as they are (no copy when float32/contiguous)."""
+    S, s_ptr = _as_host(searchPoints)
+    R, r_ptr = _as_host(referencePoints)
+    if k is None:
+        k = int(S.shape[-1])
+    m = S.size // k if hasattr(S, "size") and not callable(S.size) else S.numel() // k
+    n = R.size // k if hasattr(R, "size") and not callable(R.size) else R.numel() // k
+    if out is None:
+        out = np.empty(m, dtype=np.int32)
+    o, o_ptr = _as_host(out, dtype="int32")
+    check(lib().nn_b200_search_host(k, m, n, s_ptr, r_ptr, o_ptr, num_gpus))
+    return out
+
+
+def _as_host(a, dtype: str = "float32"):
+    """(object kept alive, raw pointer) for a numpy array or a torch CPU tensor."""
+    if hasattr(a, "data_ptr"):  # torch tensor
+        if a.is_cuda:
+            raise ValueError("host entry point takes host buffers; use multicore_hw2_b200.device for CUDA tensors")
+        a = a.contiguous()
+        return a, a.data_ptr()
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a, a.ctypes.data
+
+
+def shard_range(n: int, num_shards: int, shard: int):
+    """(begin, count) of a contiguous reference shard (v8's partition, core.cu:875-883)."""
+    b, c = ctypes.c_int64(), ctypes.c_int64()
+    check(lib().nn_b200_shard_range(n, num_shards, shard, ctypes.byref(b), ctypes.byref(c)))
+    return b.value, c.value
+
+
+def device_count(n: int = 1 << 30) -> int:
+    return lib().nn_b200_device_count(n)
+
+
+def launch_count() -> int:
+    return lib().nn_b200_launch_count()
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().nn_b200_set_option(name.encode(), int(value)))
+
+
+def describe_plan(k: int, m: int, n: int) -> str:
+    buf = ctypes.create_string_buffer(512)
+    check(lib().nn_b200_describe_plan(k, m, n, buf, 512))
+    return buf.value.decode()
+
+
+def probe_fp32(packed: bool = False, iters: int = 20000) -> float:
+    """Measured non-fused FP32 issue rate of the current device, lane-ops/s (roofline denominator)."""
+    v = ctypes.c_double()
+    check(lib().nn_b200_probe_fp32(1 if packed else 0, iters, ctypes.byref(v)))
+    return v.value

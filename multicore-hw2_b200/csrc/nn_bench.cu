@@ -1,0 +1,356 @@
+// nn_bench.cu -- standalone sweep tool for the device-resident search (links libnn_b200.so through
+// the C ABI only).  Prints one JSON line per measured configuration.  Used to pick tile shapes and
+// to produce the ncu captures under profiles/; bench.py is the contract benchmark.
+//
+//   nn_bench --k 16 --m 4096 --n 1048576 [--variant 1] [--q 4] [--scalar 1] [--splits S] [--waves W]
+//            [--iters 10] [--warmup 3] [--check 1] [--soa 1] [--repack 1] [--rreg_ctas C]
+//   nn_bench --sweep <name>     (preset lists: math, cfgs, small, repack)
+#include "../../include/nn_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define CK(call)                                                                                                       \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess)                                                                                        \
+        {                                                                                                              \
+            fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__);                  \
+            exit(2);                                                                                                   \
+        }                                                                                                              \
+    } while (0)
+#define NN(call)                                                                                                       \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        int r__ = (call);                                                                                              \
+        if (r__ != 0)                                                                                                  \
+        {                                                                                                              \
+            fprintf(stderr, "nn_b200 error %d (%s) at %s:%d\n", r__, nn_b200_last_error(), __FILE__, __LINE__);        \
+            exit(3);                                                                                                   \
+        }                                                                                                              \
+    } while (0)
+
+// counter-based uniform [0,1) floats with 24 random bits (splitmix64 finaliser)
+__global__ void fill_uniform(float *out, size_t count, uint64_t seed)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride)
+    {
+        uint64_t z = seed + (uint64_t)i * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        out[i] = (float)(z >> 40) * (1.0f / 16777216.0f);
+    }
+}
+// coarse grid: plenty of exact ties
+__global__ void quantize(float *x, size_t count, float levels)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride)
+        x[i] = floorf(x[i] * levels) / levels;
+}
+
+struct Cfg
+{
+    int k = 16, m = 4096;
+    long long n = 1 << 20;
+    int variant = 0, q = 0, scalar = 0, splits = 0, waves = 4, iters = 10, warmup = 3, check = 0, soa = 0, repack = 0,
+        rreg_ctas = 0, quant = 0;
+    std::string tag;
+};
+
+static double g_peak_ops = 0, g_clock_ghz = 0;
+static int g_sms = 0;
+
+static void run(const Cfg &c)
+{
+    const size_t ns = (size_t)c.m * c.k, nr = (size_t)c.n * c.k;
+    float *dS, *dR, *dRs = nullptr;
+    uint64_t *dK, *dK2;
+    CK(cudaMalloc(&dS, std::max<size_t>(ns, 4) * 4));
+    CK(cudaMalloc(&dR, std::max<size_t>(nr, 4) * 4));
+    CK(cudaMalloc(&dK, std::max(c.m, 1) * 8));
+    CK(cudaMalloc(&dK2, std::max(c.m, 1) * 8));
+    fill_uniform<<<1024, 256>>>(dS, ns, 1000);
+    fill_uniform<<<4096, 256>>>(dR, nr, 2000);
+    if (c.quant)
+    {
+        quantize<<<1024, 256>>>(dS, ns, (float)c.quant);
+        quantize<<<4096, 256>>>(dR, nr, (float)c.quant);
+    }
+    CK(cudaDeviceSynchronize());
+
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    std::vector<float> ms;
+
+    if (c.repack)
+    {
+        CK(cudaMalloc(&dRs, std::max<size_t>(nr, 4) * 4));
+        for (int it = 0; it < c.warmup + c.iters; ++it)
+        {
+            CK(cudaEventRecord(e0));
+            NN(nn_b200_repack_soa(c.k, c.n, dR, dRs, nullptr));
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float t;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            if (it >= c.warmup)
+                ms.push_back(t);
+        }
+        std::sort(ms.begin(), ms.end());
+        const double med = ms[ms.size() / 2], best = ms[0];
+        const double bytes = 2.0 * (double)nr * 4.0;
+        printf("{\"op\":\"repack_soa\",\"tag\":\"%s\",\"k\":%d,\"n\":%lld,\"ms_med\":%.4f,\"ms_best\":%.4f,"
+               "\"GBps_med\":%.1f,\"GBps_best\":%.1f}\n",
+               c.tag.c_str(), c.k, c.n, med, best, bytes / med / 1e6, bytes / best / 1e6);
+        fflush(stdout);
+        CK(cudaFree(dRs));
+        CK(cudaFree(dS));
+        CK(cudaFree(dR));
+        CK(cudaFree(dK));
+        CK(cudaFree(dK2));
+        return;
+    }
+    if (c.soa)
+    {
+        CK(cudaMalloc(&dRs, std::max<size_t>(nr, 4) * 4));
+        NN(nn_b200_repack_soa(c.k, c.n, dR, dRs, nullptr));
+    }
+
+    NN(nn_b200_set_option("variant", c.variant));
+    NN(nn_b200_set_option("qreg_q", c.q));
+    NN(nn_b200_set_option("scalar_math", c.scalar));
+    NN(nn_b200_set_option("splits", c.splits));
+    NN(nn_b200_set_option("waves", c.waves));
+    NN(nn_b200_set_option("rreg_ctas_per_sm", c.rreg_ctas));
+    char plan[256] = "";
+    if (!c.soa)
+        NN(nn_b200_describe_plan(c.k, c.m, c.n, plan, sizeof plan));
+
+    for (int it = 0; it < c.warmup + c.iters; ++it)
+    {
+        NN(nn_b200_keys_init(dK, c.m, nullptr));
+        CK(cudaEventRecord(e0));
+        if (c.soa)
+            NN(nn_b200_nearest_keys_soa(c.k, c.m, c.n, dS, dRs, 0, dK, nullptr));
+        else
+            NN(nn_b200_nearest_keys(c.k, c.m, c.n, dS, dR, 0, dK, nullptr));
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float t;
+        CK(cudaEventElapsedTime(&t, e0, e1));
+        if (it >= c.warmup)
+            ms.push_back(t);
+    }
+    CK(cudaGetLastError());
+    std::sort(ms.begin(), ms.end());
+    const double med = ms[ms.size() / 2], best = ms[0];
+    const double pairs = (double)c.m * (double)c.n;
+    const double ops = 3.0 * c.k * pairs;
+    const double bytes = (double)nr * 4.0;
+
+    long long mismatches = -1;
+    if (c.check)
+    {
+        NN(nn_b200_set_option("variant", 3));
+        NN(nn_b200_keys_init(dK2, c.m, nullptr));
+        NN(nn_b200_nearest_keys(c.k, c.m, c.n, dS, dR, 0, dK2, nullptr));
+        CK(cudaDeviceSynchronize());
+        std::vector<uint64_t> a(c.m), b(c.m);
+        CK(cudaMemcpy(a.data(), dK, (size_t)c.m * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(b.data(), dK2, (size_t)c.m * 8, cudaMemcpyDeviceToHost));
+        mismatches = 0;
+        for (int i = 0; i < c.m; ++i)
+            if (a[i] != b[i])
+            {
+                if (mismatches < 4)
+                    fprintf(stderr, "  mismatch q=%d got %016llx want %016llx\n", i, (unsigned long long)a[i],
+                            (unsigned long long)b[i]);
+                ++mismatches;
+            }
+        NN(nn_b200_set_option("variant", c.variant));
+    }
+
+    printf("{\"op\":\"nearest_keys\",\"tag\":\"%s\",\"k\":%d,\"m\":%d,\"n\":%lld,\"soa\":%d,\"quant\":%d,\"ms_med\":%.4f,"
+           "\"ms_best\":%.4f,\"pairs_per_s\":%.4e,\"fp32_frac_maxclk\":%.4f,\"GBps\":%.1f,\"mismatch_vs_plain\":%lld,"
+           "\"plan\":\"%s\"}\n",
+           c.tag.c_str(), c.k, c.m, c.n, c.soa, c.quant, med, best, pairs / (med * 1e-3), ops / (med * 1e-3) / g_peak_ops,
+           bytes / med / 1e6, mismatches, plan);
+    fflush(stdout);
+    if (dRs)
+        CK(cudaFree(dRs));
+    CK(cudaFree(dS));
+    CK(cudaFree(dR));
+    CK(cudaFree(dK));
+    CK(cudaFree(dK2));
+}
+
+int main(int argc, char **argv)
+{
+    Cfg c;
+    std::string sweep;
+    for (int i = 1; i < argc; ++i)
+    {
+        const std::string a = argv[i];
+        auto val = [&]() -> const char * { return (i + 1 < argc) ? argv[++i] : "0"; };
+        if (a == "--k")
+            c.k = atoi(val());
+        else if (a == "--m")
+            c.m = atoi(val());
+        else if (a == "--n")
+            c.n = atoll(val());
+        else if (a == "--variant")
+            c.variant = atoi(val());
+        else if (a == "--q")
+            c.q = atoi(val());
+        else if (a == "--scalar")
+            c.scalar = atoi(val());
+        else if (a == "--splits")
+            c.splits = atoi(val());
+        else if (a == "--waves")
+            c.waves = atoi(val());
+        else if (a == "--iters")
+            c.iters = atoi(val());
+        else if (a == "--warmup")
+            c.warmup = atoi(val());
+        else if (a == "--check")
+            c.check = atoi(val());
+        else if (a == "--soa")
+            c.soa = atoi(val());
+        else if (a == "--repack")
+            c.repack = atoi(val());
+        else if (a == "--rreg_ctas")
+            c.rreg_ctas = atoi(val());
+        else if (a == "--quant")
+            c.quant = atoi(val());
+        else if (a == "--sweep")
+            sweep = val();
+        else
+        {
+            fprintf(stderr, "unknown argument %s\n", a.c_str());
+            return 1;
+        }
+    }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    int clock_khz = 0;
+    CK(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, 0));
+    g_sms = prop.multiProcessorCount;
+    g_clock_ghz = clock_khz / 1e6;
+    g_peak_ops = (double)g_sms * 128.0 * clock_khz * 1e3;
+    printf("{\"device\":\"%s\",\"sms\":%d,\"max_clock_ghz\":%.3f,\"fp32_peak_ops\":%.4e}\n", prop.name, g_sms,
+           g_clock_ghz, g_peak_ops);
+
+    if (sweep.empty())
+    {
+        c.tag = "single";
+        run(c);
+        return 0;
+    }
+    std::vector<Cfg> list;
+    auto add = [&](const char *tag, int k, int m, long long n, int variant, int q, int scalar, int waves, int check,
+                   int soa = 0, int repack = 0, int rreg_ctas = 0, int splits = 0) {
+        Cfg x;
+        x.tag = tag;
+        x.k = k;
+        x.m = m;
+        x.n = n;
+        x.variant = variant;
+        x.q = q;
+        x.scalar = scalar;
+        x.waves = waves;
+        x.check = check;
+        x.soa = soa;
+        x.repack = repack;
+        x.rreg_ctas = rreg_ctas;
+        x.splits = splits;
+        x.iters = c.iters;
+        x.warmup = c.warmup;
+        list.push_back(x);
+    };
+    if (sweep == "math")
+    {
+        // packed f32x2 vs scalar, queries per thread, at the FP32-bound shapes
+        for (int scalar = 0; scalar < 2; ++scalar)
+        {
+            for (int q : {1, 2, 4})
+                add("k16", 16, 4096, 1 << 20, 1, q, scalar, 4, 0);
+            for (int q : {2, 4, 8})
+                add("k8", 8, 4096, 1 << 20, 1, q, scalar, 4, 0);
+            for (int q : {2, 4, 8})
+                add("k3", 3, 16384, 1 << 20, 1, q, scalar, 4, 0);
+        }
+        for (int w : {1, 2, 8})
+            add("k16-waves", 16, 4096, 1 << 20, 1, 0, 0, w, 0);
+    }
+    else if (sweep == "cfgs")
+    {
+        add("cfg1", 3, 1024, 65536, 0, 0, 0, 4, 1);
+        add("cfg2", 16, 4096, 1 << 20, 0, 0, 0, 4, 1);
+        add("cfg3", 8, 8, 1 << 26, 0, 0, 0, 4, 1);
+        add("cfg5-1/16", 3, 1 << 16, 1 << 20, 0, 0, 0, 4, 0);
+        add("cfg4-1/64", 16, 65536, 1 << 18, 0, 0, 0, 4, 0);
+    }
+    else if (sweep == "small")
+    {
+        for (int ctas : {0, 1, 2, 3, 4})
+            add("cfg3-rreg", 8, 8, 1 << 26, 2, 0, 0, 4, 0, 0, 0, ctas);
+        add("cfg3-rreg-soa", 8, 8, 1 << 26, 2, 0, 0, 4, 0, 1);
+        for (int m : {1, 2, 4, 8, 16, 32, 64})
+            add("k8-m", 8, m, 1 << 24, 2, 0, 0, 4, 0);
+        for (int m : {16, 32, 64, 128, 256, 512})
+            add("k8-m-qreg", 8, m, 1 << 24, 1, 0, 0, 4, 0);
+        for (int k : {3, 16})
+            for (int m : {1, 8})
+                add("k-m", k, m, 1 << 24, 2, 0, 0, 4, 0);
+    }
+    else if (sweep == "repack")
+    {
+        for (int k : {3, 8, 16})
+            add("repack", k, 1, 1 << 26, 0, 0, 0, 4, 0, 0, 1);
+        add("repack", 16, 1, (1 << 24) + 3, 0, 0, 0, 4, 0, 0, 1);
+    }
+    else if (sweep == "check")
+    {
+        // correctness against the plain kernel on tie-heavy data, all k, awkward sizes
+        for (int k = 3; k <= 16; ++k)
+        {
+            Cfg x;
+            x.tag = "check";
+            x.k = k;
+            x.m = 1000 + k;
+            x.n = 200000 + 37 * k;
+            x.variant = 1;
+            x.check = 1;
+            x.quant = 8;
+            x.iters = 1;
+            x.warmup = 0;
+            list.push_back(x);
+            x.variant = 2;
+            x.m = 15;
+            list.push_back(x);
+            x.soa = 1;
+            list.push_back(x);
+        }
+    }
+    else
+    {
+        fprintf(stderr, "unknown sweep %s\n", sweep.c_str());
+        return 1;
+    }
+    for (const Cfg &x : list)
+        run(x);
+    return 0;
+}

@@ -1,0 +1,896 @@
+// nn_host.cu -- host side of the B200 brute-force 1-NN path: launch planning, the C ABI of
+// include/nn_b200.h and the drop-in `cudaCallback` (replaces v8::cudaCallback / v7::cudaCallback,
+// /root/reference/sources/src/core.cu:856-958 and 710-788).
+//
+// Differences from the reference's orchestration, by design:
+//   * no transpose pass and no thrust: references are searched in the AoS layout they arrive in;
+//   * the host->device copy of the reference set is chunked on a copy stream and overlapped with
+//     the search of the previous chunk (min-folding makes chunks independent), instead of one
+//     synchronous thrust::device_vector construction (core.cu:885-891);
+//   * per-GPU candidates are merged on the devices with ncclAllReduce(min, uint64) on packed keys,
+//     not on the host (core.cu:925-957) -- and the merge is correct for m > 1;
+//   * device buffers, streams and communicators live in a lazily created context that survives
+//     across calls (the reference re-allocates per call and hides a 30 ms cold start with its
+//     static WarmUP object, core.cu:1274);
+//   * no CPU fallback (core.cu:869-870 falls back to v0): without a GPU the call fails loudly.
+#include "../../include/nn_b200.h"
+#include "nn_launch.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace nnb200;
+
+// ---------------------------------------------------------------------------------------------
+// errors, options, counters
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string t_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err = buf;
+    return code;
+}
+#define CU(call)                                                                                                       \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess)                                                                                        \
+            return fail(NN_B200_ECUDA, "%s:%d: %s -> code %d, reason: %s", __FILE__, __LINE__, #call, (int)e__,        \
+                        cudaGetErrorString(e__));                                                                      \
+    } while (0)
+
+struct Options
+{
+    std::atomic<int64_t> variant{0};         // 0 auto, 1 qreg, 2 rreg, 3 plain
+    std::atomic<int64_t> splits{0};          // qreg reference splits per query tile (0 auto)
+    std::atomic<int64_t> qreg_q{0};          // qreg queries per thread (0 auto)
+    std::atomic<int64_t> scalar_math{0};     // 1: scalar FADD/FMUL instead of packed f32x2 (A/B only)
+    std::atomic<int64_t> rreg_max_m{48};     // m <= this -> reference-register kernel
+    std::atomic<int64_t> rreg_ctas_per_sm{0}; // 0: occupancy
+    std::atomic<int64_t> h2d_chunk_bytes{16 << 20};
+    std::atomic<int64_t> waves{4};           // qreg: target CTA waves
+};
+static Options g_opt;
+
+extern "C" int nn_b200_set_option(const char *name, int64_t value)
+{
+    if (!name)
+        return fail(NN_B200_EINVAL, "null option name");
+    const std::string s(name);
+    if (s == "variant")
+        g_opt.variant = value;
+    else if (s == "splits")
+        g_opt.splits = value;
+    else if (s == "qreg_q")
+        g_opt.qreg_q = value;
+    else if (s == "scalar_math")
+        g_opt.scalar_math = value;
+    else if (s == "rreg_max_m")
+        g_opt.rreg_max_m = value;
+    else if (s == "rreg_ctas_per_sm")
+        g_opt.rreg_ctas_per_sm = value;
+    else if (s == "h2d_chunk_bytes")
+        g_opt.h2d_chunk_bytes = value;
+    else if (s == "waves")
+        g_opt.waves = value;
+    else
+        return fail(NN_B200_EINVAL, "unknown option '%s'", name);
+    return NN_B200_OK;
+}
+
+extern "C" const char *nn_b200_last_error(void) { return t_err.c_str(); }
+extern "C" int64_t nn_b200_launch_count(void) { return g_launches.load(); }
+
+// ---------------------------------------------------------------------------------------------
+// per-k dispatch
+// ---------------------------------------------------------------------------------------------
+#define NN_FOR_K(X) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+
+static cudaError_t k_launch_qreg(int k, int q, int nt, const QregArgs &a, uint32_t qtiles, cudaStream_t st)
+{
+    switch (k)
+    {
+#define X(KK)                                                                                                          \
+    case KK:                                                                                                           \
+        return launch_qreg<KK>(q, nt, a, qtiles, st);
+        NN_FOR_K(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+static cudaError_t k_query_qreg(int k, int q, int nt, LaunchInfo *li, int *tq, int *tr)
+{
+    switch (k)
+    {
+#define X(KK)                                                                                                          \
+    case KK:                                                                                                           \
+        return query_qreg<KK>(q, nt, li, tq, tr);
+        NN_FOR_K(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+static cudaError_t k_launch_rreg(int k, int mq, bool soa, const RregArgs &a, dim3 grid, cudaStream_t st)
+{
+    switch (k)
+    {
+#define X(KK)                                                                                                          \
+    case KK:                                                                                                           \
+        return launch_rreg<KK>(mq, soa, a, grid, st);
+        NN_FOR_K(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+static cudaError_t k_query_rreg(int k, int mq, bool soa, LaunchInfo *li, int *rpb)
+{
+    switch (k)
+    {
+#define X(KK)                                                                                                          \
+    case KK:                                                                                                           \
+        return query_rreg<KK>(mq, soa, li, rpb);
+        NN_FOR_K(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+static cudaError_t k_launch_plain(int k, const float *S, const float *R, int m, uint32_t n, uint32_t base,
+                                  uint32_t splits, unsigned long long *keys, cudaStream_t st)
+{
+    switch (k)
+    {
+#define X(KK)                                                                                                          \
+    case KK:                                                                                                           \
+        return launch_plain<KK>(S, R, m, n, base, splits, keys, st);
+        NN_FOR_K(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+static cudaError_t k_launch_repack(int k, const float *in, float *out, uint32_t n, int sms, cudaStream_t st)
+{
+    switch (k)
+    {
+#define X(KK)                                                                                                          \
+    case KK:                                                                                                           \
+        return launch_repack_soa<KK>(in, out, n, sms, st);
+        NN_FOR_K(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels: key init / unpack
+// ---------------------------------------------------------------------------------------------
+__global__ void nn_keys_init_kernel(unsigned long long *keys, int m)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m)
+        keys[i] = NN_B200_KEY_INIT;
+}
+__global__ void nn_keys_unpack_kernel(const unsigned long long *__restrict__ keys, int m, int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m)
+        out[i] = (int)(unsigned int)(keys[i] & 0xffffffffull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device properties (cached per device)
+// ---------------------------------------------------------------------------------------------
+struct DevInfo
+{
+    bool ok = false;
+    int sms = 0;
+    int cc = 0;
+};
+static std::mutex g_dev_mu;
+static DevInfo g_dev[64];
+
+static int dev_info(int dev, DevInfo *out)
+{
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (dev < 0 || dev >= 64)
+        return fail(NN_B200_EINVAL, "device ordinal %d out of range", dev);
+    if (!g_dev[dev].ok)
+    {
+        int sms = 0, major = 0, minor = 0;
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        CU(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+        g_dev[dev].sms = sms;
+        g_dev[dev].cc = major * 10 + minor;
+        g_dev[dev].ok = true;
+    }
+    *out = g_dev[dev];
+    if (out->cc != 100)
+        return fail(NN_B200_ENODEV, "device %d has compute capability %d.%d; this library is built for sm_100a only",
+                    dev, out->cc / 10, out->cc % 10);
+    return NN_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch planning
+// ---------------------------------------------------------------------------------------------
+struct Plan
+{
+    int variant = 0; // 1 qreg, 2 rreg, 3 plain
+    // qreg
+    int q = 0, scalar = 0, tile_q = 0, tile_r = 0, occ = 0, regs = 0;
+    uint32_t qtiles = 0, splits = 0, tiles_per_split = 0;
+    // rreg
+    int rreg_ctas = 0;
+    // plain
+    uint32_t plain_splits = 1;
+};
+
+static int make_plan(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan *p)
+{
+    int variant = (int)g_opt.variant.load();
+    if (soa)
+        variant = 2;
+    if (variant == 0)
+        variant = (m <= g_opt.rreg_max_m.load()) ? 2 : 1;
+    p->variant = variant;
+    if (variant == 1)
+    {
+        // choose queries/thread: the widest tile whose padding waste is within 3% of the best
+        const int scalar = g_opt.scalar_math.load() ? 1 : 0;
+        int cand[4] = {0, 4, 2, 1}; // 0 = wide default for this k
+        int best_q = -1, best_tile = 0;
+        double best_eff = -1.0;
+        LaunchInfo best_li{};
+        int best_tr = 0;
+        const int forced = (int)g_opt.qreg_q.load();
+        for (int ci = 0; ci < 4; ++ci)
+        {
+            const int qs = forced ? forced : cand[ci];
+            LaunchInfo li{};
+            int tq = 0, tr = 0;
+            cudaError_t e = k_query_qreg(k, qs, scalar, &li, &tq, &tr);
+            if (e != cudaSuccess)
+            {
+                if (forced)
+                    return fail(NN_B200_EINVAL, "qreg_q=%d is not built for k=%d", forced, k);
+                (void)cudaGetLastError();
+                continue;
+            }
+            const int64_t tiles = ((int64_t)m + tq - 1) / tq;
+            const double eff = (double)m / (double)(tiles * tq);
+            if (eff > best_eff * 1.03 || (best_q < 0))
+            {
+                best_eff = eff;
+                best_q = qs;
+                best_tile = tq;
+                best_li = li;
+                best_tr = tr;
+            }
+            if (forced)
+                break;
+        }
+        if (best_q < 0)
+            return fail(NN_B200_ECUDA, "no query-register kernel available for k=%d", k);
+        p->q = best_q;
+        p->scalar = scalar;
+        p->tile_q = best_tile;
+        p->tile_r = best_tr;
+        p->occ = best_li.occ > 0 ? best_li.occ : 1;
+        p->regs = best_li.regs;
+        p->qtiles = (uint32_t)(((int64_t)m + best_tile - 1) / best_tile);
+        const uint32_t full_tiles = (uint32_t)(n / best_tr);
+        const int64_t resident = (int64_t)di.sms * p->occ;
+        uint32_t splits = 1;
+        if (g_opt.splits.load() > 0)
+            splits = (uint32_t)g_opt.splits.load();
+        else
+        {
+            // total CTAs = qtiles*splits should fill W whole waves of `resident` CTAs; pick the W
+            // (up to `waves`) with the least idle tail, preferring more waves on ties
+            const uint32_t max_splits = std::max<uint32_t>(1u, full_tiles / 4u);
+            double best = -1.0;
+            const int64_t wmax = std::max<int64_t>(1, g_opt.waves.load());
+            for (int64_t w = 1; w <= wmax * 4; ++w)
+            {
+                int64_t s = (resident * w) / p->qtiles;
+                if (s < 1)
+                    continue;
+                if (s > max_splits)
+                    s = max_splits;
+                const int64_t total = s * p->qtiles;
+                const int64_t waves = (total + resident - 1) / resident;
+                const double eff = (double)total / (double)(waves * resident);
+                // mild preference for ~`waves` waves: dynamic CTA scheduling evens out variance
+                const double score = eff - 0.002 * (double)std::llabs(waves - wmax);
+                if (score > best)
+                {
+                    best = score;
+                    splits = (uint32_t)s;
+                }
+                if (s == max_splits)
+                    break;
+            }
+        }
+        if (full_tiles == 0)
+        {
+            p->splits = 1;
+            p->tiles_per_split = 0;
+        }
+        else
+        {
+            splits = std::min<uint32_t>(splits, full_tiles);
+            p->tiles_per_split = (full_tiles + splits - 1) / splits;
+            p->splits = (full_tiles + p->tiles_per_split - 1) / p->tiles_per_split;
+        }
+    }
+    else if (variant == 2)
+    {
+        LaunchInfo li{};
+        int rpb = 0;
+        cudaError_t e = k_query_rreg(k, 8, soa, &li, &rpb);
+        if (e != cudaSuccess)
+            return fail(NN_B200_ECUDA, "reference-register kernel query failed for k=%d: %s", k, cudaGetErrorString(e));
+        int per_sm = (int)g_opt.rreg_ctas_per_sm.load();
+        if (per_sm <= 0)
+            per_sm = li.occ > 0 ? li.occ : 1;
+        p->occ = per_sm;
+        p->regs = li.regs;
+        p->rreg_ctas = di.sms * per_sm;
+    }
+    else if (variant == 3)
+    {
+        const int64_t qblocks = ((int64_t)m + 127) / 128;
+        int64_t s = ((int64_t)di.sms * 16 + qblocks - 1) / qblocks;
+        s = std::max<int64_t>(1, std::min<int64_t>(s, std::max<int64_t>(1, n / 256)));
+        p->plain_splits = (uint32_t)s;
+    }
+    else
+        return fail(NN_B200_EINVAL, "unknown variant %d", variant);
+    return NN_B200_OK;
+}
+
+static int check_shape(int k, int m, int64_t n)
+{
+    if (k < NN_B200_KMIN || k > NN_B200_KMAX)
+        return fail(NN_B200_EINVAL, "k=%d outside %d..%d", k, NN_B200_KMIN, NN_B200_KMAX);
+    if (m < 0 || n < 0)
+        return fail(NN_B200_EINVAL, "negative size m=%d n=%lld", m, (long long)n);
+    if (n > 0x7fffffffLL)
+        return fail(NN_B200_EINVAL, "n=%lld does not fit the reference's int interface", (long long)n);
+    return NN_B200_OK;
+}
+
+static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const float *d_R, uint32_t index_base,
+                             uint64_t *d_keys, void *stream, bool soa)
+{
+    int rc = check_shape(k, m, n);
+    if (rc)
+        return rc;
+    if (m == 0 || n == 0)
+        return NN_B200_OK;
+    if (!d_S || !d_R || !d_keys)
+        return fail(NN_B200_EINVAL, "null device pointer");
+    if ((reinterpret_cast<uintptr_t>(d_R) & 15) != 0)
+        return fail(NN_B200_EINVAL, "reference pointer must be 16-byte aligned");
+    if ((uint64_t)index_base + (uint64_t)n > 0x100000000ull)
+        return fail(NN_B200_EINVAL, "index_base + n exceeds 32 bits");
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    DevInfo di;
+    rc = dev_info(dev, &di);
+    if (rc)
+        return rc;
+    Plan p;
+    rc = make_plan(k, m, n, soa, di, &p);
+    if (rc)
+        return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(d_keys);
+    if (p.variant == 1)
+    {
+        QregArgs a;
+        a.S = d_S;
+        a.R = d_R;
+        a.m = m;
+        a.n = (uint32_t)n;
+        a.index_base = index_base;
+        a.splits = p.splits;
+        a.tiles_per_split = p.tiles_per_split;
+        a.keys = keys;
+        CU(k_launch_qreg(k, p.q, p.scalar, a, p.qtiles, st));
+        g_launches++;
+    }
+    else if (p.variant == 2)
+    {
+        int q0 = 0;
+        const int mqs[4] = {8, 4, 2, 1};
+        for (int i = 0; i < 4; ++i)
+        {
+            const int mq = mqs[i];
+            const int passes = (m - q0) / mq;
+            if (passes == 0)
+                continue;
+            // gridDim.y is limited to 65535 passes per launch
+            int done = 0;
+            while (done < passes)
+            {
+                const int py = std::min(passes - done, 65535);
+                RregArgs a;
+                a.S = d_S + (size_t)(q0 + done * mq) * k;
+                a.R = d_R;
+                a.mq_total = py * mq;
+                a.n = (uint32_t)n;
+                a.index_base = index_base;
+                a.keys = keys + q0 + done * mq;
+                CU(k_launch_rreg(k, mq, soa, a, dim3((unsigned)p.rreg_ctas, (unsigned)py), st));
+                g_launches++;
+                done += py;
+            }
+            q0 += passes * mq;
+        }
+    }
+    else
+    {
+        CU(k_launch_plain(k, d_S, d_R, m, (uint32_t)n, index_base, p.plain_splits, keys, st));
+        g_launches++;
+    }
+    return NN_B200_OK;
+}
+
+extern "C" int nn_b200_nearest_keys(int k, int m, int64_t n, const float *d_S, const float *d_R, uint32_t index_base,
+                                    uint64_t *d_keys, void *stream)
+{
+    return nearest_keys_impl(k, m, n, d_S, d_R, index_base, d_keys, stream, false);
+}
+
+extern "C" int nn_b200_nearest_keys_soa(int k, int m, int64_t n, const float *d_S, const float *d_R_soa,
+                                        uint32_t index_base, uint64_t *d_keys, void *stream)
+{
+    return nearest_keys_impl(k, m, n, d_S, d_R_soa, index_base, d_keys, stream, true);
+}
+
+extern "C" int nn_b200_describe_plan(int k, int m, int64_t n, char *buf, size_t len)
+{
+    int rc = check_shape(k, m, n);
+    if (rc)
+        return rc;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    DevInfo di;
+    rc = dev_info(dev, &di);
+    if (rc)
+        return rc;
+    Plan p;
+    rc = make_plan(k, m, n, false, di, &p);
+    if (rc)
+        return rc;
+    if (p.variant == 1)
+        snprintf(buf, len,
+                 "qreg k=%d Q=%d %s tile=%dq x %dr regs=%d occ=%d qtiles=%u splits=%u tiles/split=%u ctas=%u sms=%d", k,
+                 p.q, p.scalar ? "scalar" : "f32x2", p.tile_q, p.tile_r, p.regs, p.occ, p.qtiles, p.splits,
+                 p.tiles_per_split, p.qtiles * p.splits, di.sms);
+    else if (p.variant == 2)
+        snprintf(buf, len, "rreg k=%d regs=%d ctas/sm=%d ctas=%d passes(8,4,2,1)=%d,%d,%d,%d sms=%d", k, p.regs, p.occ,
+                 p.rreg_ctas, m / 8, (m % 8) / 4, (m % 4) / 2, m % 2, di.sms);
+    else
+        snprintf(buf, len, "plain k=%d splits=%u sms=%d", k, p.plain_splits, di.sms);
+    return NN_B200_OK;
+}
+
+extern "C" int nn_b200_keys_init(uint64_t *d_keys, int m, void *stream)
+{
+    if (m < 0)
+        return fail(NN_B200_EINVAL, "negative m");
+    if (m == 0)
+        return NN_B200_OK;
+    if (!d_keys)
+        return fail(NN_B200_EINVAL, "null keys pointer");
+    nn_keys_init_kernel<<<(m + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long *>(d_keys),
+                                                                           m);
+    CU(cudaGetLastError());
+    g_launches++;
+    return NN_B200_OK;
+}
+
+extern "C" int nn_b200_keys_unpack(const uint64_t *d_keys, int m, int *d_results, void *stream)
+{
+    if (m < 0)
+        return fail(NN_B200_EINVAL, "negative m");
+    if (m == 0)
+        return NN_B200_OK;
+    if (!d_keys || !d_results)
+        return fail(NN_B200_EINVAL, "null pointer");
+    nn_keys_unpack_kernel<<<(m + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const unsigned long long *>(d_keys), m, d_results);
+    CU(cudaGetLastError());
+    g_launches++;
+    return NN_B200_OK;
+}
+
+extern "C" int nn_b200_repack_soa(int k, int64_t n, const float *d_in, float *d_out, void *stream)
+{
+    int rc = check_shape(k, 0, n);
+    if (rc)
+        return rc;
+    if (n == 0)
+        return NN_B200_OK;
+    if (!d_in || !d_out)
+        return fail(NN_B200_EINVAL, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) != 0)
+        return fail(NN_B200_EINVAL, "input pointer must be 16-byte aligned");
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    DevInfo di;
+    rc = dev_info(dev, &di);
+    if (rc)
+        return rc;
+    CU(k_launch_repack(k, d_in, d_out, (uint32_t)n, di.sms, (cudaStream_t)stream));
+    g_launches++;
+    return NN_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sharding helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int nn_b200_shard_range(int64_t n, int num_shards, int shard, int64_t *begin, int64_t *count)
+{
+    if (n < 0 || num_shards < 1 || shard < 0 || shard >= num_shards || !begin || !count)
+        return fail(NN_B200_EINVAL, "bad shard arguments");
+    // ceil(n / shards) like core.cu:875, rounded up to 4 points so every shard start is 16-byte
+    // aligned for any k; the last shards take the remainder and may be empty.
+    int64_t per = (n + num_shards - 1) / num_shards;
+    per = (per + 3) / 4 * 4;
+    const int64_t b = std::min<int64_t>(n, per * shard);
+    const int64_t e = std::min<int64_t>(n, b + per);
+    *begin = b;
+    *count = e - b;
+    return NN_B200_OK;
+}
+
+static int visible_devices()
+{
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return cnt;
+}
+
+extern "C" int nn_b200_device_count(int64_t n)
+{
+    int cnt = visible_devices();
+    const char *cap = getenv("NN_B200_GPUS");
+    if (cap && atoi(cap) > 0)
+        cnt = std::min(cnt, atoi(cap));
+    if ((int64_t)cnt > n) // core.cu:867-868
+        cnt = (int)std::max<int64_t>(n, 1);
+    return cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound lazily with dlopen so that single-GPU use never loads it
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+typedef struct ncclComm *ncclComm_t;
+typedef int ncclResult_t;
+// values fixed by nccl.h's public enums (NCCL 2.x): ncclUint64 = 5, ncclMin = 3
+constexpr int kNcclUint64 = 5;
+constexpr int kNcclMin = 3;
+struct Nccl
+{
+    void *h = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+Nccl g_nccl;
+
+int load_nccl()
+{
+    if (g_nccl.h)
+        return NN_B200_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names)
+    {
+        g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h)
+            break;
+    }
+    if (!g_nccl.h)
+        return fail(NN_B200_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                                               \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.h, name);                                                                 \
+    if (!g_nccl.field)                                                                                                 \
+        return fail(NN_B200_ENCCL, "libnccl lacks %s", name);
+    SYM(CommInitAll, "ncclCommInitAll")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return NN_B200_OK;
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// lazily created per-process context for the host entry point
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+struct DevCtx
+{
+    int dev = -1;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    std::vector<cudaEvent_t> events;
+    float *dS = nullptr, *dR = nullptr;
+    unsigned long long *dKeys = nullptr;
+    int *dOut = nullptr;
+    size_t capS = 0, capR = 0, capM = 0;
+    int *hOut = nullptr; // pinned
+    size_t capH = 0;
+};
+struct HostCtx
+{
+    std::mutex mu;
+    std::vector<DevCtx> devs;
+    std::vector<ncclComm_t> comms; // for the current device count
+    int comm_gpus = 0;
+};
+HostCtx g_ctx;
+
+int ensure_dev(DevCtx &c, int dev, size_t bytesS, size_t bytesR, size_t m, size_t nevents)
+{
+    CU(cudaSetDevice(dev));
+    if (c.dev != dev)
+    {
+        c.dev = dev;
+        CU(cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+    }
+    while (c.events.size() < nevents)
+    {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c.events.push_back(e);
+    }
+    if (bytesS > c.capS)
+    {
+        if (c.dS)
+            CU(cudaFree(c.dS));
+        c.dS = nullptr;
+        c.capS = 0;
+        CU(cudaMalloc(&c.dS, bytesS));
+        c.capS = bytesS;
+    }
+    if (bytesR > c.capR)
+    {
+        if (c.dR)
+            CU(cudaFree(c.dR));
+        c.dR = nullptr;
+        c.capR = 0;
+        CU(cudaMalloc(&c.dR, bytesR));
+        c.capR = bytesR;
+    }
+    if (m > c.capM)
+    {
+        if (c.dKeys)
+            CU(cudaFree(c.dKeys));
+        if (c.dOut)
+            CU(cudaFree(c.dOut));
+        c.dKeys = nullptr;
+        c.dOut = nullptr;
+        c.capM = 0;
+        CU(cudaMalloc(&c.dKeys, m * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c.dOut, m * sizeof(int)));
+        c.capM = m;
+    }
+    if (m > c.capH)
+    {
+        if (c.hOut)
+            CU(cudaFreeHost(c.hOut));
+        c.hOut = nullptr;
+        c.capH = 0;
+        CU(cudaMallocHost(&c.hOut, m * sizeof(int)));
+        c.capH = m;
+    }
+    return NN_B200_OK;
+}
+
+// Enqueue one device's share: queries, its contiguous reference shard in chunks (copy stream)
+// and one search per chunk (compute stream).  Returns without synchronising.
+int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float *R, int64_t begin, int64_t count)
+{
+    const size_t bytesS = (size_t)m * k * sizeof(float);
+    const size_t bytesR = (size_t)count * k * sizeof(float);
+    int64_t chunk_refs = std::max<int64_t>(4096, g_opt.h2d_chunk_bytes.load() / (int64_t)(k * sizeof(float)));
+    chunk_refs = chunk_refs / 4096 * 4096; // keeps every chunk start 16-byte aligned and tile aligned
+    const size_t nchunks = count > 0 ? (size_t)((count + chunk_refs - 1) / chunk_refs) : 0;
+    int rc = ensure_dev(c, dev, std::max<size_t>(bytesS, 16), std::max<size_t>(bytesR, 16), (size_t)std::max(m, 1),
+                        nchunks + 1);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(c.dS, S, bytesS, cudaMemcpyHostToDevice, c.copy));
+    CU(cudaEventRecord(c.events[0], c.copy));
+    rc = nn_b200_keys_init(reinterpret_cast<uint64_t *>(c.dKeys), m, c.compute);
+    if (rc)
+        return rc;
+    CU(cudaStreamWaitEvent(c.compute, c.events[0], 0));
+    for (size_t ci = 0; ci < nchunks; ++ci)
+    {
+        const int64_t off = (int64_t)ci * chunk_refs;
+        const int64_t cnt = std::min<int64_t>(chunk_refs, count - off);
+        CU(cudaMemcpyAsync(c.dR + (size_t)off * k, R + (size_t)(begin + off) * k, (size_t)cnt * k * sizeof(float),
+                           cudaMemcpyHostToDevice, c.copy));
+        CU(cudaEventRecord(c.events[ci + 1], c.copy));
+        CU(cudaStreamWaitEvent(c.compute, c.events[ci + 1], 0));
+        rc = nn_b200_nearest_keys(k, m, cnt, c.dS, c.dR + (size_t)off * k, (uint32_t)(begin + off),
+                                  reinterpret_cast<uint64_t *>(c.dKeys), c.compute);
+        if (rc)
+            return rc;
+    }
+    return NN_B200_OK;
+}
+
+int ensure_comms(int gpus)
+{
+    if (g_ctx.comm_gpus == gpus)
+        return NN_B200_OK;
+    int rc = load_nccl();
+    if (rc)
+        return rc;
+    for (ncclComm_t c : g_ctx.comms)
+        g_nccl.CommDestroy(c);
+    g_ctx.comms.assign(gpus, nullptr);
+    g_ctx.comm_gpus = 0;
+    std::vector<int> devs(gpus);
+    for (int i = 0; i < gpus; ++i)
+        devs[i] = i;
+    ncclResult_t r = g_nccl.CommInitAll(g_ctx.comms.data(), gpus, devs.data());
+    if (r != 0)
+        return fail(NN_B200_ENCCL, "ncclCommInitAll(%d) failed: %s", gpus, g_nccl.GetErrorString(r));
+    g_ctx.comm_gpus = gpus;
+    return NN_B200_OK;
+}
+} // namespace
+
+extern "C" int nn_b200_search_host(int k, int m, int n, const float *S, const float *R, int *results, int num_gpus)
+{
+    int rc = check_shape(k, m, n);
+    if (rc)
+        return rc;
+    if (m == 0)
+        return NN_B200_OK;
+    if (!S || !results || (n > 0 && !R))
+        return fail(NN_B200_EINVAL, "null host pointer");
+    int gpus = nn_b200_device_count(n > 0 ? n : 1);
+    if (gpus < 1)
+        return fail(NN_B200_ENODEV, "no CUDA device visible (this build has no CPU fallback)");
+    if (num_gpus > 0)
+        gpus = std::min(gpus, num_gpus);
+
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    int prev_dev = 0;
+    CU(cudaGetDevice(&prev_dev));
+    if ((int)g_ctx.devs.size() < gpus)
+        g_ctx.devs.resize(gpus);
+
+    std::vector<int> rcs(gpus, 0);
+    std::vector<std::string> errs(gpus);
+    auto work = [&](int g) {
+        int64_t b = 0, cnt = 0;
+        nn_b200_shard_range(n, gpus, g, &b, &cnt);
+        rcs[g] = enqueue_device(g_ctx.devs[g], g, k, m, S, R, b, cnt);
+        if (rcs[g])
+            errs[g] = t_err;
+    };
+    if (gpus == 1)
+        work(0);
+    else
+    {
+        // one host thread per GPU, as v8 does with OpenMP (core.cu:873): pageable copies block the
+        // issuing thread, so the shards are pushed in parallel
+        std::vector<std::thread> th;
+        for (int g = 0; g < gpus; ++g)
+            th.emplace_back(work, g);
+        for (auto &t : th)
+            t.join();
+    }
+    for (int g = 0; g < gpus; ++g)
+        if (rcs[g])
+        {
+            t_err = errs[g];
+            for (int h = 0; h < gpus; ++h)
+                if (g_ctx.devs[h].compute)
+                {
+                    cudaSetDevice(h);
+                    cudaDeviceSynchronize();
+                }
+            cudaSetDevice(prev_dev);
+            return rcs[g];
+        }
+
+    if (gpus > 1)
+    {
+        rc = ensure_comms(gpus);
+        if (rc)
+            return rc;
+        g_nccl.GroupStart();
+        for (int g = 0; g < gpus; ++g)
+        {
+            DevCtx &c = g_ctx.devs[g];
+            ncclResult_t r =
+                g_nccl.AllReduce(c.dKeys, c.dKeys, (size_t)m, kNcclUint64, kNcclMin, g_ctx.comms[g], c.compute);
+            if (r != 0)
+            {
+                g_nccl.GroupEnd();
+                return fail(NN_B200_ENCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+            }
+        }
+        ncclResult_t r = g_nccl.GroupEnd();
+        if (r != 0)
+            return fail(NN_B200_ENCCL, "ncclGroupEnd failed: %s", g_nccl.GetErrorString(r));
+    }
+
+    DevCtx &c0 = g_ctx.devs[0];
+    CU(cudaSetDevice(0));
+    rc = nn_b200_keys_unpack(reinterpret_cast<uint64_t *>(c0.dKeys), m, c0.dOut, c0.compute);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(c0.hOut, c0.dOut, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c0.compute));
+    for (int g = gpus - 1; g >= 0; --g)
+    {
+        CU(cudaSetDevice(g));
+        CU(cudaStreamSynchronize(g_ctx.devs[g].copy));
+        CU(cudaStreamSynchronize(g_ctx.devs[g].compute));
+    }
+    memcpy(results, c0.hOut, (size_t)m * sizeof(int));
+    CU(cudaSetDevice(prev_dev));
+    return NN_B200_OK;
+}
+
+extern "C" void nn_b200_cudaCallback(int k, int m, int n, float *searchPoints, float *referencePoints, int **results)
+{
+    int *tmp = (int *)malloc(sizeof(int) * (size_t)(m > 0 ? m : 1)); // caller frees (core.cu:935; main.cu:98)
+    if (!tmp)
+    {
+        printf("Error: %s:%d, malloc of %d results failed\n", __FILE__, __LINE__, m);
+        exit(1);
+    }
+    const int rc = nn_b200_search_host(k, m, n, searchPoints, referencePoints, tmp, 0);
+    if (rc != NN_B200_OK)
+    {
+        // same behaviour as the reference's CHECK macro (core.h:77-87)
+        printf("Error: %s:%d, code:%d, reason: %s \n", __FILE__, __LINE__, rc, nn_b200_last_error());
+        exit(1);
+    }
+    *results = tmp;
+}
+
+// The reference's C++-linkage entry point (core.h:71, core.cu:1282-1297).
+void cudaCallback(int k, int m, int n, float *searchPoints, float *referencePoints, int **results)
+{
+    nn_b200_cudaCallback(k, m, n, searchPoints, referencePoints, results);
+}

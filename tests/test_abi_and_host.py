@@ -1,0 +1,90 @@
+"""CPU-side checks: the C-ABI library loads and exports exactly what include/nn_b200.h declares,
+host-side helpers behave, the product never touches oracle/, and without a GPU the compute entry
+points fail loudly (no fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def nn():
+    import multicore_hw2_b200 as nn
+    if not os.path.exists(nn.LIB_PATH):
+        nn.build()
+    nn.lib()
+    return nn
+
+
+def test_library_exports_every_declared_symbol(nn):
+    hdr = open(os.path.join(ROOT, "include", "nn_b200.h")).read()
+    declared = set(re.findall(r"NN_B200_API\s+[\w\s\*]+?\b(nn_b200_\w+)\s*\(", hdr))
+    from multicore_hw2_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), "python signatures and header disagree"
+    L = ctypes.CDLL(nn.LIB_PATH)
+    for name in declared:
+        assert getattr(L, name) is not None
+    # the reference's own C++-linkage entry point (core.h:71) must be there for main.cu to link
+    assert getattr(L, _lib.CXX_SYMBOL) is not None
+    out = subprocess.run(["nm", "-D", "--defined-only", nn.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert exported == declared | {_lib.CXX_SYMBOL}, "unexpected exported symbols"
+
+
+def test_no_fused_multiply_add_in_device_code(nn):
+    """v0's arithmetic is non-fused; the shipped SASS must not contain FFMA/FFMA2 anywhere."""
+    sass = subprocess.run(["cuobjdump", "-sass", nn.LIB_PATH], capture_output=True, text=True).stdout
+    ops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", sass, flags=re.M)
+    assert len(ops) > 10000
+    assert not [o for o in ops if o.startswith("FFMA")]
+    assert "FADD2" in ops and "FMUL2" in ops      # packed f32x2 math is what runs
+    assert "UBLKCP" in ops                         # TMA bulk copy feeds the reference tiles
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", nn.LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_shard_range_partitions_like_v8(nn):
+    for n in (0, 1, 5, 1000, 65536, (1 << 24) + 3):
+        for g in (1, 2, 3, 4, 8):
+            got = [nn.shard_range(n, g, r) for r in range(g)]
+            assert got[0][0] == 0 and sum(c for _, c in got) == n
+            for (b0, c0), (b1, _) in zip(got, got[1:]):
+                assert b0 + c0 == b1
+            assert all(b % 4 == 0 or c == 0 for b, c in got)
+            per = -(-n // g)
+            assert max(c for _, c in got) <= per + 3   # core.cu:875's ceil(n/G), rounded to 4 points
+    with pytest.raises(nn.NNError):
+        nn.shard_range(10, 0, 0)
+
+
+def test_no_gpu_means_loud_failure_not_fallback(nn):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(nn.NNError) as e:
+        nn.search_host(np.zeros((2, 3), np.float32), np.ones((4, 3), np.float32))
+    assert e.value.code == -4
+    assert nn.device_count() == 0
+
+
+def test_bad_arguments(nn):
+    with pytest.raises(nn.NNError):
+        nn.set_option("no_such_option", 1)
+    with pytest.raises(ValueError):
+        nn.cudaCallback(3, 2, 2, np.zeros(5, np.float32), np.zeros(6, np.float32))
+
+
+def test_product_never_references_the_oracle():
+    bad = []
+    for base in ("multicore-hw2_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile", ".txt")):
+                    txt = open(os.path.join(dp, f), errors="replace").read()
+                    if re.search(r"(import\s+oracle|from\s+oracle|oracle/|liboracle|libref_|nn_oracle)", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

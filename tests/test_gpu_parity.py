@@ -1,0 +1,225 @@
+"""Parity of the CUDA path (through the C ABI, libnn_b200.so) against the CPU oracle and the
+committed reference fixtures.  Bit-exact: indices AND packed keys (distance bits) must be equal.
+Run on the B200 box: python -m pytest tests -m gpu."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TA = json.load(open(os.path.join(GOLD, "ta_results.json")))
+REF = json.load(open(os.path.join(GOLD, "ref_v0_cases.json")))
+
+VARIANTS = {"auto": 0, "qreg": 1, "rreg": 2, "plain": 3}
+
+
+@pytest.fixture(scope="module")
+def nn():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("gpu test collected without a CUDA device")
+    import multicore_hw2_b200 as nn
+    nn.lib()
+    yield nn
+    nn.set_option("variant", 0)
+    nn.set_option("qreg_q", 0)
+    nn.set_option("scalar_math", 0)
+
+
+def gpu_keys(nn, S, R, variant="auto", soa=False, index_base=0, q=0, scalar=0):
+    import torch
+    from multicore_hw2_b200 import device
+    nn.set_option("variant", VARIANTS[variant])
+    nn.set_option("qreg_q", q)
+    nn.set_option("scalar_math", scalar)
+    try:
+        dS = torch.from_numpy(np.ascontiguousarray(S)).cuda()
+        dR = torch.from_numpy(np.ascontiguousarray(R)).cuda()
+        keys = device.new_keys(S.shape[0])
+        if soa:
+            device.nearest_keys_soa(dS, device.repack_soa(dR), keys, index_base)
+        else:
+            device.nearest_keys(dS, dR, keys, index_base)
+        torch.cuda.synchronize()
+        return keys.cpu().numpy().view(np.uint64)
+    finally:
+        nn.set_option("variant", 0)
+        nn.set_option("qreg_q", 0)
+        nn.set_option("scalar_math", 0)
+
+
+@pytest.mark.parametrize("variant", ["auto", "qreg", "rreg", "plain"])
+@pytest.mark.parametrize("case", REF["cases"], ids=lambda c: f"{c['kind']}-k{c['k']}-m{c['m']}-n{c['n']}")
+def test_reference_v0_fixture(nn, oracle, case, variant):
+    """Indices equal the reference's own v0 outputs (fixture); keys equal the oracle's."""
+    S, R = cases.make(case["kind"], case["seed"], case["k"], case["m"], case["n"])
+    keys = gpu_keys(nn, S, R, variant)
+    assert (keys & 0xFFFFFFFF).astype(np.int64).tolist() == case["indices"]
+    assert np.array_equal(keys, oracle.keys(S, R))
+
+
+@pytest.mark.parametrize("case", [c for c in REF["cases"] if c["kind"] in ("twins", "quantized", "specials")],
+                         ids=lambda c: f"{c['kind']}-k{c['k']}")
+def test_soa_path_and_scalar_math(nn, oracle, case):
+    S, R = cases.make(case["kind"], case["seed"], case["k"], case["m"], case["n"])
+    want = oracle.keys(S, R)
+    assert np.array_equal(gpu_keys(nn, S, R, soa=True), want)
+    assert np.array_equal(gpu_keys(nn, S, R, "qreg", scalar=1), want)
+    for q in (1, 2):
+        assert np.array_equal(gpu_keys(nn, S, R, "qreg", q=q), want)
+
+
+@pytest.mark.parametrize("sample", range(8))
+def test_ta_samples_through_cudaCallback(nn, oracle, sample):
+    """The reference's eight TA samples (main.cu:28-39, seed 1000) through the drop-in entry
+    point, against the reference's golden results.csv."""
+    k, m, n = oracle.ta_shape(sample)
+    S, R = oracle.ta_sample(sample)
+    got = nn.cudaCallback(k, m, n, S, R)
+    assert got.dtype == np.int32 and got.tolist() == TA["indices"][sample]
+
+
+@pytest.mark.parametrize("k", [3, 5, 8, 16])
+def test_shards_and_chunks_fold_to_the_same_keys(nn, oracle, k):
+    """Feeding the reference set in pieces with global index bases (what shards and H2D chunks do)
+    gives exactly the keys of one call; duplicates straddle the piece boundaries."""
+    import torch
+    from multicore_hw2_b200 import device
+    S, R = cases.make("duplicated", 900 + k, k, 301, 20011)
+    want = oracle.keys(S, R)
+    dS, dR = torch.from_numpy(S).cuda(), torch.from_numpy(R).cuda()
+    for pieces in (2, 3, 8):
+        keys = device.new_keys(S.shape[0])
+        for p in reversed(range(pieces)):  # order must not matter
+            b, c = nn.shard_range(R.shape[0], pieces, p)
+            if c:
+                device.nearest_keys(dS, dR[b:b + c], keys, b)
+        assert np.array_equal(keys.cpu().numpy().view(np.uint64), want)
+        assert np.array_equal(device.keys_unpack(keys).cpu().numpy(), (want & 0xFFFFFFFF).astype(np.int32))
+
+
+@pytest.mark.parametrize("k,n", [(3, 10007), (7, 4096), (8, 5001), (16, 3000), (13, 1)])
+def test_repack_soa_matches_mat_inv(nn, oracle, k, n):
+    import torch
+    from multicore_hw2_b200 import device
+    R = np.random.default_rng(k * 31 + n).random((n, k), dtype=np.float32)
+    got = device.repack_soa(torch.from_numpy(R).cuda()).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), oracle.repack_soa(R).view(np.uint32))
+
+
+def test_edge_shapes(nn, oracle):
+    import torch
+    from multicore_hw2_b200 import device
+    # n = 0: every query keeps v0's start state -> index 0 (core.cu:39-40)
+    out = nn.search_host(np.zeros((5, 3), np.float32), np.zeros((0, 3), np.float32), k=3)
+    assert out.tolist() == [0] * 5
+    assert nn.search_host(np.zeros((0, 3), np.float32), np.zeros((4, 3), np.float32), k=3).size == 0
+    for k, m, n in [(3, 1, 1), (16, 1, 1), (4, 2, 3), (9, 1, 5), (16, 129, 2), (3, 1, 2)]:
+        S, R = cases.make("quantized", k + m + n, k, m, n)
+        assert np.array_equal(nn.search_host(S, R), oracle.v0(S, R)), (k, m, n)
+    with pytest.raises(nn.NNError):
+        nn.search_host(np.zeros((1, 2), np.float32), np.zeros((1, 2), np.float32), k=2)
+    with pytest.raises(nn.NNError):
+        nn.search_host(np.zeros((1, 17), np.float32), np.zeros((1, 17), np.float32), k=17)
+    # misaligned reference pointer is refused, not mis-read
+    S = torch.zeros((4, 3), device="cuda")
+    R = torch.zeros((9, 3), device="cuda")
+    with pytest.raises(nn.NNError):
+        device.nearest_keys(S, R.view(-1)[1:25].view(8, 3), device.new_keys(4))
+
+
+# ---- BASELINE.json sizes ---------------------------------------------------------------------------
+
+def _device_uniform(seed, rows, k):
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    return torch.rand((rows, k), generator=g, device="cuda", dtype=torch.float32)
+
+
+def _check_subset_against_oracle(nn, oracle, dS, dR, keys, rows):
+    S = dS[rows].cpu().numpy()
+    R = dR.cpu().numpy()
+    want = oracle.keys(S, R)
+    got = keys[rows].cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, want)
+
+
+def test_config1_is_ta_sample_6(nn, oracle):
+    """BASELINE config 1 (k=3, m=1024, n=65536) = TA sample 6 = results.csv line 13."""
+    S, R = oracle.ta_sample(6)
+    assert nn.cudaCallback(3, 1024, 65536, S, R).tolist() == TA["indices"][6]
+    assert (gpu_keys(nn, S, R) & 0xFFFFFFFF).tolist() == TA["indices"][6]
+
+
+def test_config2_full_size(nn, oracle):
+    """k=16, m=4096, n=2^20: oracle on 96 queries; tuned kernel == plain kernel on all 4096."""
+    import torch
+    from multicore_hw2_b200 import device
+    dS, dR = _device_uniform(1002, 4096, 16), _device_uniform(2002, 1 << 20, 16)
+    keys = device.nearest_keys(dS, dR, device.new_keys(4096))
+    nn.set_option("variant", 3)
+    plain = device.nearest_keys(dS, dR, device.new_keys(4096))
+    nn.set_option("variant", 0)
+    assert torch.equal(keys, plain)
+    rows = torch.arange(0, 4096, 43, device="cuda")
+    _check_subset_against_oracle(nn, oracle, dS, dR, keys, rows)
+
+
+def test_config3_full_size(nn, oracle):
+    """k=8, m=8, n=2^26: all 8 queries against the oracle (all host threads)."""
+    from multicore_hw2_b200 import device
+    dS, dR = _device_uniform(1003, 8, 8), _device_uniform(2003, 1 << 26, 8)
+    keys = device.nearest_keys(dS, dR, device.new_keys(8))
+    _check_subset_against_oracle(nn, oracle, dS, dR, keys, list(range(8)))
+    del dR
+
+
+def test_config5_ties_properties(nn, oracle):
+    """k=3, m=n=2^20 on an 8-bit grid (every distance is tied many times over):
+    * each query that is itself a reference must return the LOWEST index holding that point;
+    * appending a copy of the reference set (indices n..2n-1) must not change any answer;
+    * a sample of queries matches the oracle."""
+    import torch
+    from multicore_hw2_b200 import device
+    n = 1 << 20
+    dR = torch.floor(_device_uniform(2005, n, 3) * 256) / 256
+    dS = dR[torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))].contiguous()
+    keys = device.nearest_keys(dS, dR, device.new_keys(n))
+    idx = device.keys_unpack(keys).long()
+    assert int((keys >> 32).max()) == 0  # distance 0 everywhere
+    assert torch.equal(dR[idx], dS)
+    # lowest index among identical points: first occurrence of each distinct row
+    code = (dR * 256).long()
+    code = (code[:, 0] << 16) | (code[:, 1] << 8) | code[:, 2]
+    first = torch.full((1 << 24,), n, dtype=torch.long, device="cuda")
+    first.scatter_reduce_(0, code, torch.arange(n, device="cuda"), reduce="amin")
+    scode = (dS * 256).long()
+    scode = (scode[:, 0] << 16) | (scode[:, 1] << 8) | scode[:, 2]
+    assert torch.equal(idx, first[scode])
+    keys2 = device.nearest_keys(dS, torch.cat([dR, dR]), device.new_keys(n))
+    assert torch.equal(keys2, keys)
+    rows = torch.arange(0, n, 16411, device="cuda")
+    _check_subset_against_oracle(nn, oracle, dS, dR, keys, rows)
+
+
+def test_config4_scaled_and_sharded(nn, oracle):
+    """k=16, m=65536 against a 2^21-reference slice of config 4 (the full 2^24 runs in bench.py),
+    fed as 8 shards with global index bases; oracle on 48 queries."""
+    import torch
+    from multicore_hw2_b200 import device
+    n = 1 << 21
+    dS, dR = _device_uniform(1004, 65536, 16), _device_uniform(2004, n, 16)
+    keys = device.new_keys(65536)
+    for p in range(8):
+        b, c = nn.shard_range(n, 8, p)
+        device.nearest_keys(dS, dR[b:b + c], keys, b)
+    whole = device.nearest_keys(dS, dR, device.new_keys(65536))
+    assert torch.equal(keys, whole)
+    rows = torch.arange(0, 65536, 1400, device="cuda")
+    _check_subset_against_oracle(nn, oracle, dS, dR, keys, rows)
