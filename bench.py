@@ -318,8 +318,8 @@ def main():
     }
     if rank == 0:
         try:
-            meas = nn.probe_fp32(packed=False)
-            meas2 = nn.probe_fp32(packed=True)
+            meas = nn.probe_fp32(0)
+            meas2 = nn.probe_fp32(1)
             line_roof["peak_measured"] = max(meas, meas2) / 1e12
             line_roof["peak_measured_scalar"] = meas / 1e12
             line_roof["peak_measured_f32x2"] = meas2 / 1e12

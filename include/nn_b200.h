@@ -120,9 +120,10 @@ NN_B200_API const char *nn_b200_last_error(void);
 NN_B200_API int nn_b200_set_option(const char *name, int64_t value);
 
 /* Measurement aid: sustained rate, in lane-operations per second, at which this device issues
- * NON-fused FP32 multiplies and adds (scalar FMUL/FADD when packed == 0, packed f32x2 FMUL2/FADD2
- * otherwise) -- the measured denominator of the FP32 roofline.  Synchronous; ~`iters` * 64 ops per thread. */
-NN_B200_API int nn_b200_probe_fp32(int packed, int iters, double *lane_ops_per_s);
+ * NON-fused FP32 multiplies and adds -- the measured denominator of the FP32 roofline.
+ * mode 0: scalar FMUL/FADD; 1: packed f32x2 FMUL2/FADD2; 2: packed and scalar alternating;
+ * 3: blocks of packed then scalar; 4: packed + FMNMX; 5: scalar + FMNMX.  Synchronous. */
+NN_B200_API int nn_b200_probe_fp32(int mode, int iters, double *lane_ops_per_s);
 
 /* Human-readable description of the launch plan nn_b200_nearest_keys would use (variant, tile,
  * grid); written into buf (NUL-terminated, truncated to len). */

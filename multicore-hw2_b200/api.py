@@ -92,8 +92,9 @@ def describe_plan(k: int, m: int, n: int) -> str:
     return buf.value.decode()
 
 
-def probe_fp32(packed: bool = False, iters: int = 20000) -> float:
-    """Measured non-fused FP32 issue rate of the current device, lane-ops/s (roofline denominator)."""
+def probe_fp32(mode: int = 0, iters: int = 20000) -> float:
+    """Measured non-fused FP32 issue rate of the current device in lane-ops/s (roofline denominator).
+    mode 0 scalar FMUL/FADD, 1 packed f32x2, 2..5 mixes (see include/nn_b200.h)."""
     v = ctypes.c_double()
-    check(lib().nn_b200_probe_fp32(1 if packed else 0, iters, ctypes.byref(v)))
+    check(lib().nn_b200_probe_fp32(int(mode), iters, ctypes.byref(v)))
     return v.value

@@ -64,8 +64,8 @@ struct Cfg
 {
     int k = 16, m = 4096;
     long long n = 1 << 20;
-    int variant = 0, q = 0, scalar = 0, splits = 0, waves = 4, iters = 10, warmup = 3, check = 0, soa = 0, repack = 0,
-        rreg_ctas = 0, quant = 0;
+    int variant = 0, q = 0, scalar = 2, splits = 0, waves = 4, iters = 10, warmup = 3, check = 0, soa = 0, repack = 0,
+        rreg_ctas = 0, quant = 0, ldg = 0;
     std::string tag;
 };
 
@@ -131,7 +131,7 @@ static void run(const Cfg &c)
 
     NN(nn_b200_set_option("variant", c.variant));
     NN(nn_b200_set_option("qreg_q", c.q));
-    NN(nn_b200_set_option("scalar_math", c.scalar));
+    NN(nn_b200_set_option("math", c.scalar));
     NN(nn_b200_set_option("splits", c.splits));
     NN(nn_b200_set_option("waves", c.waves));
     NN(nn_b200_set_option("rreg_ctas_per_sm", c.rreg_ctas));
@@ -215,7 +215,7 @@ int main(int argc, char **argv)
             c.variant = atoi(val());
         else if (a == "--q")
             c.q = atoi(val());
-        else if (a == "--scalar")
+        else if (a == "--math")
             c.scalar = atoi(val());
         else if (a == "--splits")
             c.splits = atoi(val());
@@ -233,6 +233,8 @@ int main(int argc, char **argv)
             c.repack = atoi(val());
         else if (a == "--rreg_ctas")
             c.rreg_ctas = atoi(val());
+        else if (a == "--ldg")
+            c.ldg = atoi(val());
         else if (a == "--quant")
             c.quant = atoi(val());
         else if (a == "--sweep")
@@ -253,6 +255,19 @@ int main(int argc, char **argv)
     printf("{\"device\":\"%s\",\"sms\":%d,\"max_clock_ghz\":%.3f,\"fp32_peak_ops\":%.4e}\n", prop.name, g_sms,
            g_clock_ghz, g_peak_ops);
 
+    if (sweep == "probe")
+    {
+        const char *names[6] = {"scalar", "packed", "packed/scalar alternating", "4 packed + 4 scalar blocks",
+                                "packed + FMNMX", "scalar + FMNMX"};
+        for (int mode = 0; mode < 6; ++mode)
+        {
+            double v = 0;
+            NN(nn_b200_probe_fp32(mode, 20000, &v));
+            printf("{\"op\":\"probe_fp32\",\"mode\":%d,\"name\":\"%s\",\"lane_ops_per_s\":%.4e,\"frac_nominal\":%.4f}\n", mode,
+                   names[mode], v, v / g_peak_ops);
+        }
+        return 0;
+    }
     if (sweep.empty())
     {
         c.tag = "single";
@@ -282,45 +297,44 @@ int main(int argc, char **argv)
     };
     if (sweep == "math")
     {
-        // packed f32x2 vs scalar, queries per thread, at the FP32-bound shapes
-        for (int scalar = 0; scalar < 2; ++scalar)
+        // math mode (2 f32x2 over query pairs, 1 f32x2 over dims, 0 scalar) x queries per thread
+        for (int math : {2, 1, 0})
         {
-            for (int q : {1, 2, 4})
-                add("k16", 16, 4096, 1 << 20, 1, q, scalar, 4, 0);
+            for (int q : {2, 4})
+                add("k16", 16, 4096, 1 << 20, 1, q, math, 4, 0);
             for (int q : {2, 4, 8})
-                add("k8", 8, 4096, 1 << 20, 1, q, scalar, 4, 0);
+                add("k8", 8, 4096, 1 << 20, 1, q, math, 4, 0);
             for (int q : {2, 4, 8})
-                add("k3", 3, 16384, 1 << 20, 1, q, scalar, 4, 0);
+                add("k3", 3, 16384, 1 << 20, 1, q, math, 4, 0);
         }
-        for (int w : {1, 2, 8})
-            add("k16-waves", 16, 4096, 1 << 20, 1, 0, 0, w, 0);
     }
     else if (sweep == "cfgs")
     {
-        add("cfg1", 3, 1024, 65536, 0, 0, 0, 4, 1);
-        add("cfg2", 16, 4096, 1 << 20, 0, 0, 0, 4, 1);
-        add("cfg3", 8, 8, 1 << 26, 0, 0, 0, 4, 1);
-        add("cfg5-1/16", 3, 1 << 16, 1 << 20, 0, 0, 0, 4, 0);
-        add("cfg4-1/64", 16, 65536, 1 << 18, 0, 0, 0, 4, 0);
+        add("cfg1", 3, 1024, 65536, 0, 0, 2, 4, 1);
+        add("cfg2", 16, 4096, 1 << 20, 0, 0, 2, 4, 1);
+        add("cfg3", 8, 8, 1 << 26, 0, 0, 2, 4, 1);
+        add("cfg5-1/16", 3, 1 << 16, 1 << 20, 0, 0, 2, 4, 0);
+        add("cfg4-1/64", 16, 65536, 1 << 18, 0, 0, 2, 4, 0);
     }
     else if (sweep == "small")
     {
         for (int ctas : {0, 1, 2, 3, 4})
-            add("cfg3-rreg", 8, 8, 1 << 26, 2, 0, 0, 4, 0, 0, 0, ctas);
-        add("cfg3-rreg-soa", 8, 8, 1 << 26, 2, 0, 0, 4, 0, 1);
+            add("cfg3-rreg", 8, 8, 1 << 26, 2, 0, 2, 4, 0, 0, 0, ctas);
+        add("cfg3-rreg-soa", 8, 8, 1 << 26, 2, 0, 2, 4, 0, 1);
+
         for (int m : {1, 2, 4, 8, 16, 32, 64})
-            add("k8-m", 8, m, 1 << 24, 2, 0, 0, 4, 0);
+            add("k8-m", 8, m, 1 << 24, 2, 0, 2, 4, 0);
         for (int m : {16, 32, 64, 128, 256, 512})
-            add("k8-m-qreg", 8, m, 1 << 24, 1, 0, 0, 4, 0);
+            add("k8-m-qreg", 8, m, 1 << 24, 1, 0, 2, 4, 0);
         for (int k : {3, 16})
             for (int m : {1, 8})
-                add("k-m", k, m, 1 << 24, 2, 0, 0, 4, 0);
+                add("k-m", k, m, 1 << 24, 2, 0, 2, 4, 0);
     }
     else if (sweep == "repack")
     {
         for (int k : {3, 8, 16})
-            add("repack", k, 1, 1 << 26, 0, 0, 0, 4, 0, 0, 1);
-        add("repack", 16, 1, (1 << 24) + 3, 0, 0, 0, 4, 0, 0, 1);
+            add("repack", k, 1, 1 << 26, 0, 0, 2, 4, 0, 0, 1);
+        add("repack", 16, 1, (1 << 24) + 3, 0, 0, 2, 4, 0, 0, 1);
     }
     else if (sweep == "check")
     {
@@ -341,6 +355,9 @@ int main(int argc, char **argv)
             x.variant = 2;
             x.m = 15;
             list.push_back(x);
+            x.m = 1;
+            list.push_back(x);
+            x.m = 15;
             x.soa = 1;
             list.push_back(x);
         }

@@ -17,6 +17,7 @@
 #include "nn_launch.h"
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -60,11 +61,11 @@ struct Options
     std::atomic<int64_t> variant{0};         // 0 auto, 1 qreg, 2 rreg, 3 plain
     std::atomic<int64_t> splits{0};          // qreg reference splits per query tile (0 auto)
     std::atomic<int64_t> qreg_q{0};          // qreg queries per thread (0 auto)
-    std::atomic<int64_t> scalar_math{0};     // 1: scalar FADD/FMUL instead of packed f32x2 (A/B only)
+    std::atomic<int64_t> math{2};            // 2 f32x2 over query pairs, 1 f32x2 over dims, 0 scalar (A/B only)
     std::atomic<int64_t> rreg_max_m{48};     // m <= this -> reference-register kernel
     std::atomic<int64_t> rreg_ctas_per_sm{0}; // 0: occupancy
     std::atomic<int64_t> h2d_chunk_bytes{16 << 20};
-    std::atomic<int64_t> waves{4};           // qreg: target CTA waves
+    std::atomic<int64_t> waves{8};           // qreg: most CTA waves considered
 };
 static Options g_opt;
 
@@ -79,8 +80,8 @@ extern "C" int nn_b200_set_option(const char *name, int64_t value)
         g_opt.splits = value;
     else if (s == "qreg_q")
         g_opt.qreg_q = value;
-    else if (s == "scalar_math")
-        g_opt.scalar_math = value;
+    else if (s == "math")
+        g_opt.math = value;
     else if (s == "rreg_max_m")
         g_opt.rreg_max_m = value;
     else if (s == "rreg_ctas_per_sm")
@@ -251,93 +252,87 @@ static int make_plan(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan 
     p->variant = variant;
     if (variant == 1)
     {
-        // choose queries/thread: the widest tile whose padding waste is within 3% of the best
-        const int scalar = g_opt.scalar_math.load() ? 1 : 0;
-        int cand[4] = {0, 4, 2, 1}; // 0 = wide default for this k
-        int best_q = -1, best_tile = 0;
-        double best_eff = -1.0;
-        LaunchInfo best_li{};
-        int best_tr = 0;
-        const int forced = (int)g_opt.qreg_q.load();
+        // Candidates: queries/thread Q (tile = 128*Q queries) x reference splits.  Each is scored with
+        // a small efficiency model -- query padding x SM fill / wave quantisation x per-split
+        // prologue amortisation x a measured per-tile-shape factor -- and the best one wins.
+        const int math = (int)g_opt.math.load();
+        const int forced_q = (int)g_opt.qreg_q.load();
+        const int64_t forced_splits = g_opt.splits.load();
+        const int cand[4] = {0, 4, 2, 1}; // 0 = wide default for this k
+        double best_score = -1.0;
         for (int ci = 0; ci < 4; ++ci)
         {
-            const int qs = forced ? forced : cand[ci];
+            const int qs = forced_q ? forced_q : cand[ci];
             LaunchInfo li{};
             int tq = 0, tr = 0;
-            cudaError_t e = k_query_qreg(k, qs, scalar, &li, &tq, &tr);
+            cudaError_t e = k_query_qreg(k, qs, math, &li, &tq, &tr);
             if (e != cudaSuccess)
             {
-                if (forced)
-                    return fail(NN_B200_EINVAL, "qreg_q=%d is not built for k=%d", forced, k);
                 (void)cudaGetLastError();
+                if (forced_q)
+                    return fail(NN_B200_EINVAL, "qreg_q=%d is not built for k=%d", forced_q, k);
                 continue;
             }
-            const int64_t tiles = ((int64_t)m + tq - 1) / tq;
-            const double eff = (double)m / (double)(tiles * tq);
-            if (eff > best_eff * 1.03 || (best_q < 0))
+            const int q = tq / 128;
+            const int occ = li.occ > 0 ? li.occ : 1;
+            const int64_t qtiles = ((int64_t)m + tq - 1) / tq;
+            const int64_t full_tiles = n / tr;
+            const int64_t resident = (int64_t)di.sms * occ;
+            const double e_pad = (double)m / (double)(qtiles * tq);
+            // tile-shape factor from the B200 sweeps (profiles/): single-query tiles cannot use the
+            // pair-packed math, 2-query tiles pay more shared-memory loads per pair when k is small
+            const double f_q = q == 1 ? 0.85 : (q == 2 && k < 8 ? 0.95 : 1.0);
+            auto score_of = [&](int64_t sp, int64_t *tps_out) {
+                const int64_t tps = full_tiles > 0 ? (full_tiles + sp - 1) / sp : 0;
+                const int64_t spl = full_tiles > 0 ? (full_tiles + tps - 1) / tps : 1;
+                const int64_t total = spl * qtiles;
+                double e_fill;
+                if (total >= resident)
+                {
+                    const int64_t waves = (total + resident - 1) / resident;
+                    e_fill = (double)total / (double)(waves * resident);
+                }
+                else // fewer CTAs than slots: the FMA pipe needs the full occupancy to stay busy
+                    e_fill = std::pow((double)total / (double)resident, 0.7);
+                const double e_amort = tps > 0 ? (double)tps / ((double)tps + 0.1) : 1.0;
+                *tps_out = tps;
+                return e_pad * e_fill * e_amort * f_q;
+            };
+            std::vector<int64_t> sc;
+            if (forced_splits > 0)
+                sc.push_back(std::min<int64_t>(forced_splits, std::max<int64_t>(1, full_tiles)));
+            else
             {
-                best_eff = eff;
-                best_q = qs;
-                best_tile = tq;
-                best_li = li;
-                best_tr = tr;
+                const int64_t wmax = std::max<int64_t>(1, g_opt.waves.load());
+                for (int64_t w = 1; w <= wmax; ++w)
+                    sc.push_back(std::min<int64_t>(std::max<int64_t>(1, full_tiles),
+                                                   std::max<int64_t>(1, (resident * w) / qtiles)));
+                sc.push_back(std::max<int64_t>(1, full_tiles));
             }
-            if (forced)
+            for (int64_t sp : sc)
+            {
+                int64_t tps = 0;
+                // tiny preference for more CTAs at equal score: dynamic scheduling evens out variance
+                const double sco = score_of(sp, &tps) + 1e-6 * (double)sp;
+                if (sco > best_score)
+                {
+                    best_score = sco;
+                    p->q = qs;
+                    p->scalar = math;
+                    p->tile_q = tq;
+                    p->tile_r = tr;
+                    p->occ = occ;
+                    p->regs = li.regs;
+                    p->qtiles = (uint32_t)qtiles;
+                    p->tiles_per_split = (uint32_t)tps;
+                    p->splits = full_tiles > 0 ? (uint32_t)((full_tiles + tps - 1) / tps) : 1u;
+                }
+            }
+            if (forced_q)
                 break;
         }
-        if (best_q < 0)
+        if (best_score < 0)
             return fail(NN_B200_ECUDA, "no query-register kernel available for k=%d", k);
-        p->q = best_q;
-        p->scalar = scalar;
-        p->tile_q = best_tile;
-        p->tile_r = best_tr;
-        p->occ = best_li.occ > 0 ? best_li.occ : 1;
-        p->regs = best_li.regs;
-        p->qtiles = (uint32_t)(((int64_t)m + best_tile - 1) / best_tile);
-        const uint32_t full_tiles = (uint32_t)(n / best_tr);
-        const int64_t resident = (int64_t)di.sms * p->occ;
-        uint32_t splits = 1;
-        if (g_opt.splits.load() > 0)
-            splits = (uint32_t)g_opt.splits.load();
-        else
-        {
-            // total CTAs = qtiles*splits should fill W whole waves of `resident` CTAs; pick the W
-            // (up to `waves`) with the least idle tail, preferring more waves on ties
-            const uint32_t max_splits = std::max<uint32_t>(1u, full_tiles / 4u);
-            double best = -1.0;
-            const int64_t wmax = std::max<int64_t>(1, g_opt.waves.load());
-            for (int64_t w = 1; w <= wmax * 4; ++w)
-            {
-                int64_t s = (resident * w) / p->qtiles;
-                if (s < 1)
-                    continue;
-                if (s > max_splits)
-                    s = max_splits;
-                const int64_t total = s * p->qtiles;
-                const int64_t waves = (total + resident - 1) / resident;
-                const double eff = (double)total / (double)(waves * resident);
-                // mild preference for ~`waves` waves: dynamic CTA scheduling evens out variance
-                const double score = eff - 0.002 * (double)std::llabs(waves - wmax);
-                if (score > best)
-                {
-                    best = score;
-                    splits = (uint32_t)s;
-                }
-                if (s == max_splits)
-                    break;
-            }
-        }
-        if (full_tiles == 0)
-        {
-            p->splits = 1;
-            p->tiles_per_split = 0;
-        }
-        else
-        {
-            splits = std::min<uint32_t>(splits, full_tiles);
-            p->tiles_per_split = (full_tiles + splits - 1) / splits;
-            p->splits = (full_tiles + p->tiles_per_split - 1) / p->tiles_per_split;
-        }
     }
     else if (variant == 2)
     {
@@ -413,36 +408,45 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
         a.splits = p.splits;
         a.tiles_per_split = p.tiles_per_split;
         a.keys = keys;
+        a.neg_zero = -0.0f;
         CU(k_launch_qreg(k, p.q, p.scalar, a, p.qtiles, st));
         g_launches++;
     }
     else if (p.variant == 2)
     {
-        int q0 = 0;
-        const int mqs[4] = {8, 4, 2, 1};
-        for (int i = 0; i < 4; ++i)
-        {
-            const int mq = mqs[i];
-            const int passes = (m - q0) / mq;
-            if (passes == 0)
-                continue;
-            // gridDim.y is limited to 65535 passes per launch
+        // full passes of 8 queries, then one pass with the smallest even width covering the tail
+        auto launch = [&](int q0, int count, int mq) -> int {
             int done = 0;
+            const int passes = (count + mq - 1) / mq;
             while (done < passes)
             {
-                const int py = std::min(passes - done, 65535);
+                const int py = std::min(passes - done, 65535); // gridDim.y limit
                 RregArgs a;
                 a.S = d_S + (size_t)(q0 + done * mq) * k;
                 a.R = d_R;
-                a.mq_total = py * mq;
+                a.mq_total = std::min(count - done * mq, py * mq);
                 a.n = (uint32_t)n;
                 a.index_base = index_base;
                 a.keys = keys + q0 + done * mq;
+                a.neg_zero = -0.0f;
                 CU(k_launch_rreg(k, mq, soa, a, dim3((unsigned)p.rreg_ctas, (unsigned)py), st));
                 g_launches++;
                 done += py;
             }
-            q0 += passes * mq;
+            return NN_B200_OK;
+        };
+        const int full = (m / 8) * 8, tail = m - full;
+        if (full)
+        {
+            rc = launch(0, full, 8);
+            if (rc)
+                return rc;
+        }
+        if (tail)
+        {
+            rc = launch(full, tail, tail > 4 ? 8 : (tail > 2 ? 4 : 2));
+            if (rc)
+                return rc;
         }
     }
     else
@@ -483,11 +487,11 @@ extern "C" int nn_b200_describe_plan(int k, int m, int64_t n, char *buf, size_t 
     if (p.variant == 1)
         snprintf(buf, len,
                  "qreg k=%d Q=%d %s tile=%dq x %dr regs=%d occ=%d qtiles=%u splits=%u tiles/split=%u ctas=%u sms=%d", k,
-                 p.q, p.scalar ? "scalar" : "f32x2", p.tile_q, p.tile_r, p.regs, p.occ, p.qtiles, p.splits,
+                 p.q, p.scalar == 0 ? "scalar" : (p.scalar == 1 ? "f32x2-dims" : "f32x2-pairs"), p.tile_q, p.tile_r, p.regs, p.occ, p.qtiles, p.splits,
                  p.tiles_per_split, p.qtiles * p.splits, di.sms);
     else if (p.variant == 2)
-        snprintf(buf, len, "rreg k=%d regs=%d ctas/sm=%d ctas=%d passes(8,4,2,1)=%d,%d,%d,%d sms=%d", k, p.regs, p.occ,
-                 p.rreg_ctas, m / 8, (m % 8) / 4, (m % 4) / 2, m % 2, di.sms);
+        snprintf(buf, len, "rreg k=%d f32x2-pairs regs=%d ctas/sm=%d ctas=%d passes8=%d tail=%d sms=%d", k, p.regs,
+                 p.occ, p.rreg_ctas, m / 8, m % 8, di.sms);
     else
         snprintf(buf, len, "plain k=%d splits=%u sms=%d", k, p.plain_splits, di.sms);
     return NN_B200_OK;

@@ -9,8 +9,20 @@
 // Arithmetic contract (v0, core.cu:44-54): d2 = ((d0*d0 + d1*d1) + d2*d2) + ... with
 // d_i = q_i - r_i, every operation IEEE round-to-nearest, never fused.  The packed
 // FADD2/FMUL2 (f32x2) forms used here are element-wise IEEE operations, so they give the same
-// bits as the scalar ones; the adds stay scalar and sequential.  `0 + d0*d0` is elided: it is
-// exact for every d0*d0 (which is never -0).
+// bits as the scalar ones; the sum over the dimensions stays sequential.  `0 + d0*d0` is elided:
+// it is exact for every d0*d0 (which is never -0).
+//
+// Math modes (MATH template parameter):
+//   0  scalar FADD/FMUL/FADD                                   (kept for A/B measurements)
+//   1  f32x2 across dimension pairs, scalar sequential adds    (kept for A/B measurements)
+//   2  f32x2 across a PAIR OF QUERIES: (qa_d, qb_d) - bcast(r_d), squared, accumulated -- every
+//      FP instruction of the hot loop is packed.  Measured on B200: streams that interleave packed
+//      and scalar FP32 instructions lose ~20% of the FMA pipe, all-packed streams reach 99%.
+// ptxas 12.9 contracts mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 although `.rn` forbids it, so
+// mode 2 writes the square as fma(d, d, -0.0) with the -0.0 passed in at run time (exact, see
+// sqdist_pair).  tests/test_abi_and_host.py asserts that the shipped SASS holds no scalar FFMA and
+// exactly one FFMA2 per (2k-1)/k FADD2 in the pair kernels (a contracted add would change the
+// ratio), and the `twins` parity family fails on any fused or re-ordered sum.
 //
 // Tie rule (strict `>` over ascending nInd, core.cu:50-54): the winner is the LOWEST index
 // among the references at minimum distance; NaN distances never win; a query that nothing
@@ -23,9 +35,30 @@
 
 #include "nn_launch.h"
 
+// build-time tuning knobs (overridable with -D for A/B builds; defaults are the measured best)
+#ifndef NN_QREG_UNROLL
+#define NN_QREG_UNROLL 1 // chunks of CH references unrolled in the tile loop
+#endif
+#ifndef NN_RREG_SLOTS
+#define NN_RREG_SLOTS 2 // register ring depth of the reference-register kernel
+#endif
+#ifndef NN_RREG_SLOT_FLOATS
+#define NN_RREG_SLOT_FLOATS 32 // reference floats per thread per ring slot
+#endif
+#ifndef NN_RREG_LDG256
+#define NN_RREG_LDG256 1 // use 256-bit global loads where a reference group is a multiple of 32 bytes
+#endif
+#ifndef NN_RREG_L2PF
+#define NN_RREG_L2PF 0 // slot-batches ahead that a CTA asks the L2 to prefetch (0 = off; no gain measured)
+#endif
+#ifndef NN_QREG_REGCAP_LOW
+#define NN_QREG_REGCAP_LOW 0 // 1: always compile the query-register kernel for 4 CTAs/SM (128 regs)
+#endif
+
 namespace nnb200
 {
 
+constexpr int kQregUnroll = NN_QREG_UNROLL;
 constexpr unsigned long long KEY_INIT = 0x7F80000000000000ull;
 constexpr uint32_t NO_REF = 0xFFFFFFFFu;
 
@@ -84,6 +117,27 @@ __device__ __forceinline__ float sqdist(const float (&q)[K], const float *r)
 #pragma unroll
     for (int i = 1; i < K; ++i)
         acc = __fadd_rn(acc, p[i]);
+    return acc;
+}
+
+// Two queries against one reference, all packed: qp[i] = (qa_i, qb_i), r broadcast to both lanes
+// (SASS: FADD2 Rd, Rq.F32x2.HI_LO, -Rr.F32).  Returns (d2(qa, r), d2(qb, r)).
+// The square is written fma(d, d, nz) with nz = (-0.0f, -0.0f) supplied at run time through the
+// kernel arguments: x*x + (-0) is x*x rounded once, bit for bit the IEEE product in every case
+// (+0 + -0 = +0 under round-to-nearest; Inf and NaN propagate), and because it already IS an fma
+// ptxas cannot contract it with the following add.  (A plain mul.rn.f32x2 feeding add.rn.f32x2 is
+// contracted to FFMA2 by ptxas 12.9 even though `.rn` forbids it; that would break parity.)
+template <int K>
+__device__ __forceinline__ float2 sqdist_pair(const float2 (&qp)[K], const float *r, const float2 nz)
+{
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+    {
+        const float2 d = __fadd2_rn(qp[i], make_float2(-r[i], -r[i]));
+        const float2 p = __ffma2_rn(d, d, nz);
+        acc = (i == 0) ? p : __fadd2_rn(acc, p);
+    }
     return acc;
 }
 
@@ -147,6 +201,23 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
+// 256-bit read-only global load (sm_100: LDG.E.256): one instruction and one L1 lookup per 32-byte
+// sector instead of two 128-bit loads that each touch the sector.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const float *p, float *dst)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(dst[0]), "=f"(dst[1]), "=f"(dst[2]), "=f"(dst[3]), "=f"(dst[4]), "=f"(dst[5]), "=f"(dst[6]),
+                   "=f"(dst[7])
+                 : "l"(p));
+}
+
+// Asks the L2 to fetch `bytes` (multiple of 16) starting at `src` from HBM; no destination, no
+// completion tracking.  One instruction per 16 KB moves the HBM latency out of the register loads.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // =============================================================================================
 // Kernel A -- "query-register" kernel, for many queries (FP32-pipe bound).
 //
@@ -170,8 +241,9 @@ struct QregCfg
     static constexpr size_t SMEM = (size_t)STAGES * TILE_BYTES + 64;
 };
 
-template <int K, int Q, bool PACKED>
-__device__ __forceinline__ void qreg_chunk(const float *__restrict__ sm, const float (&q)[Q][K], float (&cm)[Q])
+template <int K, int Q, int MATH>
+__device__ __forceinline__ void qreg_chunk(const float *__restrict__ sm, const float (&q)[Q][K], float (&cm)[Q],
+                                           const float2 nz)
 {
     constexpr int G = Geo<K>::G, F4 = Geo<K>::F4, CH = QregCfg<K>::CH;
     float hold[Q];
@@ -193,23 +265,52 @@ __device__ __forceinline__ void qreg_chunk(const float *__restrict__ sm, const f
         for (int g = 0; g < G; ++g)
         {
             const int c = g0 + g;
+            float dist[Q];
+            if constexpr (MATH == 2)
+            {
+                static_assert(MATH != 2 || Q % 2 == 0, "pair-packed math needs an even number of queries per thread");
+#pragma unroll
+                for (int j = 0; j < Q; j += 2)
+                {
+                    float2 qp[K];
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+                        qp[i] = make_float2(q[j][i], q[j + 1][i]);
+                    const float2 d2 = sqdist_pair<K>(qp, &grp[g * K], nz);
+                    dist[j] = d2.x;
+                    dist[j + 1] = d2.y;
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int j = 0; j < Q; ++j)
+                    dist[j] = sqdist_par<K, MATH == 1>(q[j], &grp[g * K], (g * K) & 1);
+            }
 #pragma unroll
             for (int j = 0; j < Q; ++j)
             {
-                const float d = sqdist_par<K, PACKED>(q[j], &grp[g * K], (g * K) & 1);
                 if ((c & 1) == 0)
-                    hold[j] = d;
+                    hold[j] = dist[j];
                 else if (c == 1)
-                    cm[j] = fminf(hold[j], d);
+                    cm[j] = fminf(hold[j], dist[j]);
                 else
-                    cm[j] = fminf(fminf(cm[j], hold[j]), d);
+                    cm[j] = fminf(fminf(cm[j], hold[j]), dist[j]);
             }
         }
     }
 }
 
-template <int K, int Q, int NT, bool PACKED>
-__global__ void __launch_bounds__(NT, 512 / NT) nn_qreg_kernel(const QregArgs a)
+// CTAs per SM the register allocation is capped for: 4 (128 registers) when the query tile and one
+// reference group fit comfortably, else 3 (168 registers) -- spilling costs more than occupancy here.
+template <int K, int Q, int MATH>
+constexpr int qreg_minb()
+{
+    return (NN_QREG_REGCAP_LOW || Q * K + Geo<K>::G * K + (MATH == 2 ? 52 : 36) <= 128) ? 4 : 3;
+}
+
+template <int K, int Q, int NT, int MATH>
+__global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(const QregArgs a)
 {
     using C = QregCfg<K>;
     constexpr int CH = C::CH, TR = C::TR, STAGES = C::STAGES;
@@ -232,6 +333,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) nn_qreg_kernel(const QregArgs a)
     float q[Q][K];
     float best[Q];
     uint32_t bref[Q];
+    const float2 nz = make_float2(a.neg_zero, a.neg_zero);
 #pragma unroll
     for (int j = 0; j < Q; ++j)
     {
@@ -284,11 +386,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) nn_qreg_kernel(const QregArgs a)
         mbar_wait(&full[stage], parity);
         const float *sm = tiles + (size_t)stage * C::TILE_FLOATS;
         const uint32_t ref0 = t * TR;
-#pragma unroll 2
+#pragma unroll kQregUnroll
         for (int c = 0; c < TR; c += CH)
         {
             float cm[Q];
-            qreg_chunk<K, Q, PACKED>(sm + c * K, q, cm);
+            qreg_chunk<K, Q, MATH>(sm + c * K, q, cm, nz);
 #pragma unroll
             for (int j = 0; j < Q; ++j)
                 if (cm[j] < best[j])
@@ -317,7 +419,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) nn_qreg_kernel(const QregArgs a)
         for (uint32_t c = 0; c < padded; c += CH)
         {
             float cm[Q];
-            qreg_chunk<K, Q, PACKED>(tiles + c * K, q, cm);
+            qreg_chunk<K, Q, MATH>(tiles + c * K, q, cm, nz);
 #pragma unroll
             for (int j = 0; j < Q; ++j)
                 if (cm[j] < best[j])
@@ -356,32 +458,51 @@ __global__ void __launch_bounds__(NT, 512 / NT) nn_qreg_kernel(const QregArgs a)
 // Kernel B -- "reference-register" kernel, for few queries (HBM-streaming / SM-fill bound).
 //
 // The roles are swapped: every thread streams its OWN references from HBM straight into registers
-// (128-bit loads from the native AoS layout, next batch prefetched while the current one is
-// computed) and all MQ queries of the pass are broadcast from shared memory.  A persistent grid
-// (SMs x occupancy CTAs) strides over the reference set, so all SMs are busy even for m = 1.
-// Per thread and query: batch minimum (FMNMX3) + strict-less select on (best, batch start); the
-// exact index is resolved at the end, keys are reduced across the warp with __shfl_xor and folded
-// with one 64-bit atomicMin per warp and query.
+// (128-bit loads from the native AoS layout) and the MQ queries of the pass are broadcast from
+// shared memory, stored there as interleaved PAIRS (qa_d, qb_d) so that the whole distance
+// computation is packed f32x2 with the thread's reference coordinate as the broadcast operand.
+// A persistent grid (SMs x occupancy CTAs) strides over the reference set, so all SMs are busy
+// even for m = 1.
+//
+// At k = 8, m = 8 the path needs the FP32 pipe AND the HBM stream near their peaks at the same
+// time, so the loads must be in flight continuously.  The thread's reference registers form a RING
+// of NS slots (PS groups each): as soon as a slot has been consumed its loads for NS slots ahead
+// are issued, so NS-1 slots are always in flight (a two-buffer scheme only has one buffer in
+// flight for part of the time; ncu showed long-scoreboard stalls dominating).  Measured dead ends,
+// both slower than plain LDG on B200: a cp.async.bulk (TMA) ring per CTA (5.2 TB/s at m = 1) and a
+// warp-private cp.async ring (3.3 TB/s at m = 1, any depth or occupancy) versus 6.2 TB/s here.
+//
+// Per thread and query: minimum over a ring round (FMNMX3) + strict-less select on (best, round);
+// the exact index is resolved at the end, keys are reduced across the warp with __shfl_xor and
+// folded with one 64-bit atomicMin per warp and query.
 // SOA = true reads references from the repacked [k][n] layout instead (coalesced 32-bit loads).
+// MQ is even; a pass over an odd tail of queries duplicates its last query (valid_q masks it).
 // =============================================================================================
-template <int K, int MQ, int PG, int NT, bool SOA, int MINB>
+template <int K, int MQ, int PS, int NS, int NT, bool SOA, int MINB>
 __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
 {
+    static_assert(MQ % 2 == 0, "queries are processed in pairs");
     constexpr int G = SOA ? 1 : Geo<K>::G;
     constexpr int F4 = G * K / 4; // (AoS only) float4 per group
-    constexpr int P = G * PG; // references per thread per batch
-    __shared__ __align__(16) float sq[MQ * K];
+    constexpr int P = G * PS;     // references per thread per slot
+    constexpr int NP = MQ / 2;    // query pairs
+    __shared__ __align__(16) float2 sq[NP * K]; // sq[pair*K + d] = (qa_d, qb_d)
 
     const int tid = threadIdx.x;
     const int pass = blockIdx.y;
-    const float *S = a.S + (size_t)pass * MQ * K;
-    unsigned long long *keys = a.keys + (size_t)pass * MQ;
-    for (int i = tid; i < MQ * K; i += NT)
-        sq[i] = __ldg(S + i);
+    const int q0 = pass * MQ;                     // first query of this pass (relative to a.S)
+    const int valid_q = min(MQ, a.mq_total - q0); // >= 1
+    for (int i = tid; i < NP * K; i += NT)
+    {
+        const int pr = i / K, d = i % K;
+        const int qa = min(2 * pr, valid_q - 1), qb = min(2 * pr + 1, valid_q - 1);
+        sq[i] = make_float2(__ldg(a.S + (size_t)(q0 + qa) * K + d), __ldg(a.S + (size_t)(q0 + qb) * K + d));
+    }
     __syncthreads();
 
     float best[MQ];
     uint32_t bref[MQ];
+    const float2 nz = make_float2(a.neg_zero, a.neg_zero);
 #pragma unroll
     for (int j = 0; j < MQ; ++j)
     {
@@ -389,18 +510,22 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
         bref[j] = NO_REF;
     }
 
-    // Batch b covers groups [b*NT*PG, (b+1)*NT*PG); thread t owns groups b*NT*PG + i*NT + t.
+    // Slot-batch sb covers groups [sb*NT*PS, (sb+1)*NT*PS); thread t owns groups sb*NT*PS + i*NT + t.
+    // This CTA's j-th slot-batch is blockIdx.x + j*gridDim.x and lives in ring slot j % NS.
     const uint32_t ngroups = (a.n + G - 1) / G;
-    const uint32_t groups_per_batch = NT * PG;
-    const uint32_t nbatches = (ngroups + groups_per_batch - 1) / groups_per_batch;
+    const uint32_t groups_per_sb = NT * PS;
+    const uint32_t nsb = (ngroups + groups_per_sb - 1) / groups_per_sb;
+    const uint32_t mine = blockIdx.x < nsb ? (nsb - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    float cur[P * K], nxt[P * K];
+    float ring[NS][P * K];
+    const bool wide = (reinterpret_cast<uintptr_t>(a.R) & 31) == 0; // 256-bit loads need 32-byte alignment
 
-    auto load_batch = [&](uint32_t b, float(&dst)[P * K]) {
+    auto load_slot = [&](uint32_t j, float(&dst)[P * K]) {
+        const uint32_t sb = blockIdx.x + j * gridDim.x;
 #pragma unroll
-        for (int i = 0; i < PG; ++i)
+        for (int i = 0; i < PS; ++i)
         {
-            const uint32_t grp = b * groups_per_batch + i * NT + tid;
+            const uint32_t grp = sb * groups_per_sb + i * NT + tid;
             const uint32_t r0 = grp * G;
             if constexpr (SOA)
             {
@@ -410,19 +535,28 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
             }
             else if (r0 + G <= a.n)
             {
-                const float4 *p4 = reinterpret_cast<const float4 *>(a.R + (size_t)r0 * K);
-#pragma unroll
-                for (int f = 0; f < F4; ++f)
+                if (NN_RREG_LDG256 && (G * K) % 8 == 0 && wide)
                 {
-                    const float4 v = __ldg(p4 + f);
-                    dst[i * G * K + 4 * f + 0] = v.x;
-                    dst[i * G * K + 4 * f + 1] = v.y;
-                    dst[i * G * K + 4 * f + 2] = v.z;
-                    dst[i * G * K + 4 * f + 3] = v.w;
+#pragma unroll
+                    for (int f = 0; f < (G * K) / 8; ++f)
+                        ldg256(a.R + (size_t)r0 * K + 8 * f, &dst[i * G * K + 8 * f]);
+                }
+                else
+                {
+                    const float4 *p4 = reinterpret_cast<const float4 *>(a.R + (size_t)r0 * K);
+#pragma unroll
+                    for (int f = 0; f < F4; ++f)
+                    {
+                        const float4 v = __ldg(p4 + f);
+                        dst[i * G * K + 4 * f + 0] = v.x;
+                        dst[i * G * K + 4 * f + 1] = v.y;
+                        dst[i * G * K + 4 * f + 2] = v.z;
+                        dst[i * G * K + 4 * f + 3] = v.w;
+                    }
                 }
             }
             else
-            {
+            { // ragged end of the reference set: slots past n are NaN (a NaN distance never wins)
 #pragma unroll
                 for (int e = 0; e < G * K; ++e)
                     dst[i * G * K + e] =
@@ -431,78 +565,89 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
         }
     };
 
-    auto compute_batch = [&](uint32_t b, const float(&ref)[P * K]) {
+    // fold one slot into the running round minima rm[]
+    auto compute_slot = [&](const float(&ref)[P * K], float (&rm)[MQ]) {
 #pragma unroll
-        for (int j = 0; j < MQ; ++j)
+        for (int pr = 0; pr < NP; ++pr)
         {
-            float qv[K];
-            if (K % 4 == 0)
+            float2 qp[K];
+            if constexpr (K % 2 == 0)
             {
-                const float4 *q4 = reinterpret_cast<const float4 *>(sq + j * K);
+                const float4 *q4 = reinterpret_cast<const float4 *>(sq + pr * K);
 #pragma unroll
-                for (int f = 0; f < K / 4; ++f)
+                for (int f = 0; f < K / 2; ++f)
                 {
                     const float4 v = q4[f];
-                    qv[4 * f + 0] = v.x;
-                    qv[4 * f + 1] = v.y;
-                    qv[4 * f + 2] = v.z;
-                    qv[4 * f + 3] = v.w;
+                    qp[2 * f] = make_float2(v.x, v.y);
+                    qp[2 * f + 1] = make_float2(v.z, v.w);
                 }
             }
             else
             {
 #pragma unroll
                 for (int d = 0; d < K; ++d)
-                    qv[d] = sq[j * K + d];
+                    qp[d] = sq[pr * K + d];
             }
-            float bm = 0.f, hold = 0.f;
+            float2 hold = make_float2(0.f, 0.f);
 #pragma unroll
             for (int p = 0; p < P; ++p)
             {
-                const float d = sqdist_par<K, true>(qv, &ref[p * K], (p * K) & 1);
-                if (p == 0)
-                    bm = d;
-                else if ((p & 1) == 1 && p + 1 < P)
+                const float2 d = sqdist_pair<K>(qp, &ref[p * K], nz);
+                if ((p & 1) == 0 && p + 1 < P)
                     hold = d;
-                else if ((p & 1) == 0)
-                    bm = fminf(fminf(bm, hold), d);
+                else if ((p & 1) == 1)
+                {
+                    rm[2 * pr] = fminf(fminf(rm[2 * pr], hold.x), d.x);
+                    rm[2 * pr + 1] = fminf(fminf(rm[2 * pr + 1], hold.y), d.y);
+                }
                 else
-                    bm = fminf(bm, d);
-            }
-            if (bm < best[j])
-            {
-                best[j] = bm;
-                bref[j] = b;
+                {
+                    rm[2 * pr] = fminf(rm[2 * pr], d.x);
+                    rm[2 * pr + 1] = fminf(rm[2 * pr + 1], d.y);
+                }
             }
         }
     };
 
-    // software pipeline over this CTA's batches: the loads of the next batch are in flight while
-    // the current one is computed; two register buffers alternate (no copies)
-    uint32_t b = blockIdx.x;
-    if (b < nbatches)
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+        if ((uint32_t)s < mine)
+            load_slot(s, ring[s]);
+
+    for (uint32_t base = 0; base < mine; base += NS)
     {
-        load_batch(b, cur);
-        for (;;)
+        float rm[MQ];
+#pragma unroll
+        for (int j = 0; j < MQ; ++j)
+            rm[j] = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
         {
-            uint32_t bn = b + gridDim.x;
-            if (bn < nbatches)
-                load_batch(bn, nxt);
-            compute_batch(b, cur);
-            if (bn >= nbatches)
-                break;
-            b = bn;
-            bn = b + gridDim.x;
-            if (bn < nbatches)
-                load_batch(bn, cur);
-            compute_batch(b, nxt);
-            if (bn >= nbatches)
-                break;
-            b = bn;
+            const uint32_t j = base + s;
+            if (j < mine)
+            {
+                if (NN_RREG_L2PF > 0 && !SOA && tid == 0 && j + NS + NN_RREG_L2PF < mine)
+                { // HBM -> L2 for the slot-batch this CTA will load into registers L2PF steps from now
+                    const uint32_t sbp = blockIdx.x + (j + NS + NN_RREG_L2PF) * gridDim.x;
+                    const size_t f0 = (size_t)sbp * groups_per_sb * G * K;
+                    if (f0 + (size_t)groups_per_sb * G * K <= (size_t)a.n * K)
+                        bulk_prefetch_l2(a.R + f0, groups_per_sb * G * K * 4u);
+                }
+                compute_slot(ring[s], rm);
+                if (j + NS < mine)
+                    load_slot(j + NS, ring[s]); // refill at once: NS-1 slots stay in flight
+            }
         }
+#pragma unroll
+        for (int j = 0; j < MQ; ++j)
+            if (rm[j] < best[j])
+            {
+                best[j] = rm[j];
+                bref[j] = base;
+            }
     }
 
-    // resolve: lowest index within this thread's winning batch (its groups ascend with i)
+    // resolve: lowest index within this thread's winning round (slot-batches ascend with s, groups with i)
     const int lane = tid & 31;
 #pragma unroll
     for (int j = 0; j < MQ; ++j)
@@ -513,24 +658,31 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
             float qv[K];
 #pragma unroll
             for (int d = 0; d < K; ++d)
-                qv[d] = sq[j * K + d];
+                qv[d] = (j & 1) ? sq[(j / 2) * K + d].y : sq[(j / 2) * K + d].x;
             uint32_t idx = 0;
-#pragma unroll
-            for (int i = PG - 1; i >= 0; --i)
+            for (int s = NS - 1; s >= 0; --s)
             {
+                const uint32_t jj = bref[j] + s;
+                if (jj >= mine)
+                    continue;
+                const uint32_t sb = blockIdx.x + jj * gridDim.x;
 #pragma unroll
-                for (int g = G - 1; g >= 0; --g)
+                for (int i = PS - 1; i >= 0; --i)
                 {
-                    const uint32_t r = (bref[j] * groups_per_batch + i * NT + tid) * G + g;
-                    if (r < a.n)
-                    {
-                        float rr[K];
 #pragma unroll
-                        for (int d = 0; d < K; ++d)
-                            rr[d] = SOA ? __ldg(a.R + (size_t)d * a.n + r) : __ldg(a.R + (size_t)r * K + d);
-                        const float d2 = sqdist<K, 0, false>(qv, rr);
-                        if (d2 == best[j])
-                            idx = r;
+                    for (int g = G - 1; g >= 0; --g)
+                    {
+                        const uint32_t r = (sb * groups_per_sb + i * NT + tid) * G + g;
+                        if (r < a.n)
+                        {
+                            float rr[K];
+#pragma unroll
+                            for (int d = 0; d < K; ++d)
+                                rr[d] = SOA ? __ldg(a.R + (size_t)d * a.n + r) : __ldg(a.R + (size_t)r * K + d);
+                            const float d2 = sqdist<K, 0, false>(qv, rr);
+                            if (d2 == best[j])
+                                idx = r;
+                        }
                     }
                 }
             }
@@ -542,8 +694,8 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
             key = other < key ? other : key;
         }
-        if (lane == 0 && key < (KEY_INIT | NO_REF))
-            atomicMin(keys + j, key);
+        if (lane == 0 && j < valid_q && key < (KEY_INIT | NO_REF))
+            atomicMin(a.keys + q0 + j, key);
     }
 }
 

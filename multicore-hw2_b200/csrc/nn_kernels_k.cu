@@ -21,10 +21,10 @@ struct QregDefault
     static constexpr int Q = BUDGET >= 8 ? 8 : (BUDGET >= 4 ? 4 : (BUDGET >= 2 ? 2 : 1));
 };
 
-template <int K, int Q, int NT, bool PACKED>
+template <int K, int Q, int NT, int MATH>
 static cudaError_t launch_qreg_one(const QregArgs &a, uint32_t qtiles, cudaStream_t st)
 {
-    auto kern = nn_qreg_kernel<K, Q, NT, PACKED>;
+    auto kern = nn_qreg_kernel<K, Q, NT, MATH>;
     static bool configured = false;
     if (!configured)
     {
@@ -37,10 +37,10 @@ static cudaError_t launch_qreg_one(const QregArgs &a, uint32_t qtiles, cudaStrea
     return cudaGetLastError();
 }
 
-template <int K, int Q, int NT, bool PACKED>
+template <int K, int Q, int NT, int MATH>
 static cudaError_t query_qreg_one(LaunchInfo *info, int *tile_queries, int *tile_refs)
 {
-    auto kern = nn_qreg_kernel<K, Q, NT, PACKED>;
+    auto kern = nn_qreg_kernel<K, Q, NT, MATH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QregCfg<K>::SMEM);
     if (e != cudaSuccess)
         return e;
@@ -62,17 +62,23 @@ static cudaError_t query_qreg_one(LaunchInfo *info, int *tile_queries, int *tile
 
 // q_sel: 0 = wide default tile, otherwise the requested queries/thread (1, 2, 4, 8; only tiles up
 // to the default width are built for a given k -- wider ones would spill).
-// nt_sel: bit 0 clear = packed f32x2 math, set = scalar math (kept for A/B measurements).
+// math: 2 = f32x2 over query pairs (default; needs Q >= 2, Q = 1 falls back to mode 1),
+//       1 = f32x2 over dimension pairs, 0 = scalar (both kept for A/B measurements).
 template <class F>
-static cudaError_t qreg_dispatch(int q_sel, int nt_sel, F f)
+static cudaError_t qreg_dispatch(int q_sel, int math, F f)
 {
     constexpr int QD = QregDefault<NN_K>::Q;
-    const bool scalar = (nt_sel & 1) != 0;
     const int qq = q_sel == 0 ? QD : q_sel;
     auto go = [&](auto qc) -> cudaError_t {
         constexpr int QV = decltype(qc)::value;
         if constexpr (QV <= QD)
-            return scalar ? f(qc, std::false_type{}) : f(qc, std::true_type{});
+        {
+            if (math == 0)
+                return f(qc, std::integral_constant<int, 0>{});
+            if (math == 1 || QV == 1)
+                return f(qc, std::integral_constant<int, 1>{});
+            return f(qc, std::integral_constant<int, (QV >= 2 ? 2 : 1)>{});
+        }
         else
             return cudaErrorInvalidValue;
     };
@@ -92,17 +98,17 @@ static cudaError_t qreg_dispatch(int q_sel, int nt_sel, F f)
 }
 
 template <>
-cudaError_t launch_qreg<NN_K>(int q_sel, int nt_sel, const QregArgs &a, uint32_t qtiles, cudaStream_t st)
+cudaError_t launch_qreg<NN_K>(int q_sel, int math, const QregArgs &a, uint32_t qtiles, cudaStream_t st)
 {
-    return qreg_dispatch(q_sel, nt_sel, [&](auto qc, auto pk) {
+    return qreg_dispatch(q_sel, math, [&](auto qc, auto pk) {
         return launch_qreg_one<NN_K, decltype(qc)::value, 128, decltype(pk)::value>(a, qtiles, st);
     });
 }
 
 template <>
-cudaError_t query_qreg<NN_K>(int q_sel, int nt_sel, LaunchInfo *info, int *tile_queries, int *tile_refs)
+cudaError_t query_qreg<NN_K>(int q_sel, int math, LaunchInfo *info, int *tile_queries, int *tile_refs)
 {
-    return qreg_dispatch(q_sel, nt_sel, [&](auto qc, auto pk) {
+    return qreg_dispatch(q_sel, math, [&](auto qc, auto pk) {
         return query_qreg_one<NN_K, decltype(qc)::value, 128, decltype(pk)::value>(info, tile_queries, tile_refs);
     });
 }
@@ -112,32 +118,39 @@ template <int K>
 struct RregCfg
 {
     static constexpr int NT = 128;
-    // groups per thread per batch: ~32 reference floats in flight per buffer
-    static constexpr int PG = (32 / (Geo<K>::G * K)) >= 1 ? (32 / (Geo<K>::G * K)) : 1;
-    static constexpr int PG_SOA = (32 / K) >= 2 ? (32 / K) : 2;
-    // CTAs per SM the register budget is compiled for: two reference buffers + per-query state
+    static constexpr int NS = NN_RREG_SLOTS;
+    // groups per thread per ring slot: ~NN_RREG_SLOT_FLOATS reference floats
+    static constexpr int PS = (NN_RREG_SLOT_FLOATS / (Geo<K>::G * K)) >= 1 ? (NN_RREG_SLOT_FLOATS / (Geo<K>::G * K)) : 1;
+    static constexpr int PS_SOA = (NN_RREG_SLOT_FLOATS / K) >= 2 ? (NN_RREG_SLOT_FLOATS / K) : 2;
+    // CTAs per SM the register budget is compiled for: the reference ring + per-query state
     static constexpr int minb(int mq, bool soa)
     {
-        const int refs = 2 * (soa ? PG_SOA : PG * Geo<K>::G) * K;
-        return (refs + 3 * mq + K + 28 <= 128) ? 4 : ((refs + 3 * mq + K + 28 <= 168) ? 3 : 2);
+        const int refs = NS * (soa ? PS_SOA : PS * Geo<K>::G) * K;
+        const int need = refs + 3 * mq + 2 * K + 30; // ring, best/bref/rm, one query pair
+#ifdef NN_RREG_FORCE_MINB
+        return NN_RREG_FORCE_MINB;
+#endif
+        // measured on B200 (k = 8, m = 8): 4 CTAs/SM at a 128-register cap beat 3 CTAs at 148
+        return need <= 136 ? 4 : (need <= 168 ? 3 : 2);
     }
 };
 
 template <int K, int MQ, bool SOA>
 static cudaError_t launch_rreg_one(const RregArgs &a, dim3 grid, cudaStream_t st)
 {
-    constexpr int PG = SOA ? RregCfg<K>::PG_SOA : RregCfg<K>::PG;
-    if (a.mq_total != (int)grid.y * MQ)
+    constexpr int PS = SOA ? RregCfg<K>::PS_SOA : RregCfg<K>::PS;
+    if ((a.mq_total + MQ - 1) / MQ != (int)grid.y || a.mq_total < 1)
         return cudaErrorInvalidValue;
-    nn_rreg_kernel<K, MQ, PG, RregCfg<K>::NT, SOA, RregCfg<K>::minb(MQ, SOA)><<<grid, RregCfg<K>::NT, 0, st>>>(a);
+    nn_rreg_kernel<K, MQ, PS, RregCfg<K>::NS, RregCfg<K>::NT, SOA, RregCfg<K>::minb(MQ, SOA)>
+        <<<grid, RregCfg<K>::NT, 0, st>>>(a);
     return cudaGetLastError();
 }
 
 template <int K, int MQ, bool SOA>
 static cudaError_t query_rreg_one(LaunchInfo *info, int *refs_per_batch)
 {
-    constexpr int PG = SOA ? RregCfg<K>::PG_SOA : RregCfg<K>::PG;
-    auto kern = nn_rreg_kernel<K, MQ, PG, RregCfg<K>::NT, SOA, RregCfg<K>::minb(MQ, SOA)>;
+    constexpr int PS = SOA ? RregCfg<K>::PS_SOA : RregCfg<K>::PS;
+    auto kern = nn_rreg_kernel<K, MQ, PS, RregCfg<K>::NS, RregCfg<K>::NT, SOA, RregCfg<K>::minb(MQ, SOA)>;
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, kern);
     if (e != cudaSuccess)
@@ -149,15 +162,13 @@ static cudaError_t query_rreg_one(LaunchInfo *info, int *refs_per_batch)
     info->regs = fa.numRegs;
     info->smem = (int)fa.sharedSizeBytes;
     info->occ = occ;
-    *refs_per_batch = RregCfg<K>::NT * PG * (SOA ? 1 : Geo<K>::G);
+    *refs_per_batch = RregCfg<K>::NT * PS * (SOA ? 1 : Geo<K>::G);
     return cudaSuccess;
 }
 
 #define NN_RREG_DISPATCH(FN, ...)                                                                                      \
     switch (mq)                                                                                                        \
     {                                                                                                                  \
-    case 1:                                                                                                            \
-        return soa ? FN<NN_K, 1, true>(__VA_ARGS__) : FN<NN_K, 1, false>(__VA_ARGS__);                                 \
     case 2:                                                                                                            \
         return soa ? FN<NN_K, 2, true>(__VA_ARGS__) : FN<NN_K, 2, false>(__VA_ARGS__);                                 \
     case 4:                                                                                                            \

@@ -18,16 +18,18 @@ struct QregArgs
     uint32_t splits;          // reference splits per query tile
     uint32_t tiles_per_split; // full tiles per split
     unsigned long long *keys;
+    float neg_zero;           // must be -0.0f: run-time addend of the exact fma(d, d, -0) square
 };
 
 struct RregArgs
 {
-    const float *S;   // queries of this launch (already offset to q0)
+    const float *S;   // queries of this launch (already offset to its first query)
     const float *R;
-    int mq_total;     // number of queries covered by this launch = gridDim.y * MQ
+    int mq_total;     // queries covered by this launch: gridDim.y = ceil(mq_total / MQ) passes
     uint32_t n;
     uint32_t index_base;
     unsigned long long *keys; // already offset to q0
+    float neg_zero;           // must be -0.0f (see QregArgs)
 };
 
 // ---- per-K launchers (defined in nn_kernels_k.cu) -----------------------------------------
@@ -39,9 +41,9 @@ struct LaunchInfo
 };
 
 template <int K>
-cudaError_t launch_qreg(int q_sel, int nt_sel, const QregArgs &a, uint32_t qtiles, cudaStream_t st);
+cudaError_t launch_qreg(int q_sel, int math, const QregArgs &a, uint32_t qtiles, cudaStream_t st);
 template <int K>
-cudaError_t query_qreg(int q_sel, int nt_sel, LaunchInfo *info, int *tile_queries, int *tile_refs);
+cudaError_t query_qreg(int q_sel, int math, LaunchInfo *info, int *tile_queries, int *tile_refs);
 template <int K>
 cudaError_t launch_rreg(int mq, bool soa, const RregArgs &a, dim3 grid, cudaStream_t st);
 template <int K>

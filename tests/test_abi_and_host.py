@@ -36,14 +36,34 @@ def test_library_exports_every_declared_symbol(nn):
     assert exported == declared | {_lib.CXX_SYMBOL}, "unexpected exported symbols"
 
 
-def test_no_fused_multiply_add_in_device_code(nn):
-    """v0's arithmetic is non-fused; the shipped SASS must not contain FFMA/FFMA2 anywhere."""
+def test_no_contracted_multiply_add_in_device_code(nn):
+    """v0's arithmetic is non-fused.  The shipped SASS may hold NO scalar FFMA at all.  The only
+    FFMA2 allowed are the exact squares fma(d, d, -0.0) of the query-pair kernels (nn_kernels.cuh,
+    sqdist_pair): there, per dimension, one FADD2 subtracts, one FFMA2 squares and (except for the
+    first dimension) one FADD2 accumulates, so FADD2 : FFMA2 must be exactly (2k-1) : k and no
+    FMUL2 may remain.  Had ptxas contracted a multiply into an add, the ratio would be off."""
     sass = subprocess.run(["cuobjdump", "-sass", nn.LIB_PATH], capture_output=True, text=True).stdout
-    ops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", sass, flags=re.M)
-    assert len(ops) > 10000
-    assert not [o for o in ops if o.startswith("FFMA")]
-    assert "FADD2" in ops and "FMUL2" in ops      # packed f32x2 math is what runs
-    assert "UBLKCP" in ops                         # TMA bulk copy feeds the reference tiles
+    funcs = re.split(r"\n\s*Function : ", sass)[1:]
+    assert len(funcs) > 100
+    seen_pair_kernels = 0
+    all_ops = set()
+    for f in funcs:
+        name = f.split("\n", 1)[0].strip()
+        ops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", f, flags=re.M)
+        all_ops.update(ops)
+        n = {o: ops.count(o) for o in ("FFMA", "FFMA2", "FADD2", "FMUL2")}
+        assert n["FFMA"] == 0, name
+        mq = re.search(r"nn_qreg_kernelILi(\d+)ELi\d+ELi\d+ELi2E", name)
+        mr = re.search(r"nn_rreg_kernelILi(\d+)E", name)
+        if mq or mr:
+            k = int((mq or mr).group(1))
+            seen_pair_kernels += 1
+            assert n["FFMA2"] > 0 and n["FMUL2"] == 0, name
+            assert n["FADD2"] * k == n["FFMA2"] * (2 * k - 1), (name, n)
+        else:
+            assert n["FFMA2"] == 0, name
+    assert seen_pair_kernels >= 14 * 2
+    assert "UBLKCP" in all_ops                     # TMA bulk copy feeds the reference tiles
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", nn.LIB_PATH], capture_output=True, text=True).stdout
 
 

@@ -28,15 +28,15 @@ def nn():
     yield nn
     nn.set_option("variant", 0)
     nn.set_option("qreg_q", 0)
-    nn.set_option("scalar_math", 0)
+    nn.set_option("math", 2)
 
 
-def gpu_keys(nn, S, R, variant="auto", soa=False, index_base=0, q=0, scalar=0):
+def gpu_keys(nn, S, R, variant="auto", soa=False, index_base=0, q=0, math=2):
     import torch
     from multicore_hw2_b200 import device
     nn.set_option("variant", VARIANTS[variant])
     nn.set_option("qreg_q", q)
-    nn.set_option("scalar_math", scalar)
+    nn.set_option("math", math)
     try:
         dS = torch.from_numpy(np.ascontiguousarray(S)).cuda()
         dR = torch.from_numpy(np.ascontiguousarray(R)).cuda()
@@ -50,7 +50,7 @@ def gpu_keys(nn, S, R, variant="auto", soa=False, index_base=0, q=0, scalar=0):
     finally:
         nn.set_option("variant", 0)
         nn.set_option("qreg_q", 0)
-        nn.set_option("scalar_math", 0)
+        nn.set_option("math", 2)
 
 
 @pytest.mark.parametrize("variant", ["auto", "qreg", "rreg", "plain"])
@@ -65,11 +65,12 @@ def test_reference_v0_fixture(nn, oracle, case, variant):
 
 @pytest.mark.parametrize("case", [c for c in REF["cases"] if c["kind"] in ("twins", "quantized", "specials")],
                          ids=lambda c: f"{c['kind']}-k{c['k']}")
-def test_soa_path_and_scalar_math(nn, oracle, case):
+def test_soa_path_and_other_math_modes(nn, oracle, case):
     S, R = cases.make(case["kind"], case["seed"], case["k"], case["m"], case["n"])
     want = oracle.keys(S, R)
     assert np.array_equal(gpu_keys(nn, S, R, soa=True), want)
-    assert np.array_equal(gpu_keys(nn, S, R, "qreg", scalar=1), want)
+    for math in (0, 1):
+        assert np.array_equal(gpu_keys(nn, S, R, "qreg", math=math), want)
     for q in (1, 2):
         assert np.array_equal(gpu_keys(nn, S, R, "qreg", q=q), want)
 
