@@ -105,7 +105,7 @@ class ClockSampler:
                         self.reasons.add(nme)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.01)
 
     def stop(self):
         self._stop.set()
@@ -234,9 +234,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # host-side rendezvous for the phases in which only rank 0 works: an NCCL barrier would leave
+        # a spinning kernel on every other GPU, and rank 0's e2e call drives those GPUs itself
+        host_group = dist.new_group(backend="gloo")
     nn.lib()
 
     k, m, n_local = WORKLOADS[args.workload]
@@ -336,6 +340,9 @@ def main():
             dist.gather(R, gathered, dst=0)
             if rank == 0:
                 Rh_parts = [g.cpu() for g in gathered]
+                del gathered
+            torch.cuda.synchronize()
+            dist.barrier(group=host_group)  # the other ranks now wait on the CPU, their GPUs are idle
         if rank == 0:
             Sh = S.cpu().pin_memory()
             Rh = torch.cat(Rh_parts).pin_memory()
@@ -355,7 +362,8 @@ def main():
                    "matches_device_resident_result": same}
             del Rh, Sh
         if world > 1:
-            dist.barrier()
+            torch.cuda.synchronize()
+            dist.barrier(group=host_group)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None

@@ -224,3 +224,22 @@ def test_config4_scaled_and_sharded(nn, oracle):
     assert torch.equal(keys, whole)
     rows = torch.arange(0, 65536, 1400, device="cuda")
     _check_subset_against_oracle(nn, oracle, dS, dR, keys, rows)
+
+
+def test_multi_gpu_host_entry(nn, oracle):
+    """v8's job: the host entry shards the references over all visible GPUs and merges the keys
+    with ncclAllReduce(min, uint64).  Needs >= 2 GPUs (gpurun --gpus 2); duplicates straddle the
+    shard boundaries so the lowest-index rule is exercised across devices."""
+    import torch
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs at least 2 GPUs")
+    for kind, k, m, n in [("duplicated", 16, 300, 40001), ("twins", 8, 200, 30011), ("quantized", 3, 1000, 5),
+                          ("uniform", 3, 1, 1)]:
+        S, R = cases.make(kind, 7000 + k, k, m, n)
+        want = oracle.v0(S, R, threads=0)
+        for gpus in sorted({2, g}):
+            assert np.array_equal(nn.search_host(S, R, num_gpus=gpus), want), (kind, gpus)
+    # same through the reference's own entry point, all GPUs
+    S, R = oracle.ta_sample(7)
+    assert nn.cudaCallback(16, 1024, 65536, S, R).tolist() == TA["indices"][7]
