@@ -312,8 +312,9 @@ static int make_plan(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan 
             for (int64_t sp : sc)
             {
                 int64_t tps = 0;
-                // tiny preference for more CTAs at equal score: dynamic scheduling evens out variance
-                const double sco = score_of(sp, &tps) + 1e-6 * (double)sp;
+                // tiny, bounded preference for more CTAs at equal score (dynamic scheduling evens out
+                // variance between SMs)
+                const double sco = score_of(sp, &tps) + 1e-4 * std::min(1.0, (double)(sp * qtiles) / (8.0 * resident));
                 if (sco > best_score)
                 {
                     best_score = sco;

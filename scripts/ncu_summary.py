@@ -19,8 +19,9 @@ for path in sys.argv[1:]:
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
     cols[path] = d
+print(f"{'metric':64s}", *[f"{p.split('/')[-1].replace('.ncu-rep','')[:21]:>22s}" for p in sys.argv[1:]])
 keys = [k for k in WANT if any(k in d for d in cols.values())]
 stall = sorted({h for d in cols.values() for h in d if 'issue_stalled' in h and h.endswith('per_issue_active.ratio')})
 for k in keys + stall:
     short = k.replace('smsp__average_warps_issue_stalled_', 'stall_').replace('_per_issue_active.ratio', '')
-    print(f"{short[:70]:70s}", *[f"{cols[p].get(k, ('-', ''))[0][:14]:>15s}" for p in sys.argv[1:]], cols[sys.argv[1]].get(k, ('', ''))[1])
+    print(f"{short[:64]:64s}", *[f"{(cols[p].get(k, ('-', ''))[0][:12] + ' ' + cols[p].get(k, ('', ''))[1][:7]):>22s}" for p in sys.argv[1:]])
