@@ -129,6 +129,12 @@ NN_B200_API int nn_b200_probe_fp32(int mode, int iters, double *lane_ops_per_s);
  * grid); written into buf (NUL-terminated, truncated to len). */
 NN_B200_API int nn_b200_describe_plan(int k, int m, int64_t n, char *buf, size_t len);
 
+/* Introspection of the launch planner (pure arithmetic, no device needed): for `qtiles` query tiles,
+ * `full_tiles` whole reference tiles and a GPU that holds `resident_ctas` CTAs at once, how many
+ * reference splits per query tile the query-register kernel is launched with. */
+NN_B200_API int nn_b200_plan_splits(int64_t qtiles, int64_t full_tiles, int64_t resident_ctas, int64_t max_waves,
+                                    int64_t *splits, int64_t *tiles_per_split);
+
 #ifdef __cplusplus
 } /* extern "C" */
 

@@ -242,6 +242,65 @@ struct Plan
     uint32_t plain_splits = 1;
 };
 
+// Pure part of the query-register plan: how many reference splits a query tile gets.  Inputs:
+// query tiles, full reference tiles, CTAs the GPU holds at once (SMs x occupancy), most waves
+// considered.  Returns the efficiency estimate (SM fill / wave quantisation x per-split prologue
+// amortisation) of the best candidate and writes its split count and tiles per split.
+static double plan_splits(int64_t qtiles, int64_t full_tiles, int64_t resident, int64_t wmax, int64_t forced,
+                          int64_t *splits_out, int64_t *tps_out)
+{
+    auto score_of = [&](int64_t sp, int64_t *spl_out, int64_t *tps) {
+        *tps = full_tiles > 0 ? (full_tiles + sp - 1) / sp : 0;
+        const int64_t spl = full_tiles > 0 ? (full_tiles + *tps - 1) / *tps : 1;
+        const int64_t total = spl * qtiles;
+        double e_fill;
+        if (total >= resident)
+        {
+            const int64_t waves = (total + resident - 1) / resident;
+            e_fill = (double)total / (double)(waves * resident);
+        }
+        else // fewer CTAs than slots: the FMA pipe needs the full occupancy to stay busy
+            e_fill = std::pow((double)total / (double)resident, 0.7);
+        const double e_amort = *tps > 0 ? (double)*tps / ((double)*tps + 0.1) : 1.0;
+        *spl_out = spl;
+        // tiny, bounded preference for more CTAs at equal score (dynamic scheduling evens out
+        // variance between SMs)
+        return e_fill * e_amort + 1e-4 * std::min(1.0, (double)total / (8.0 * (double)resident));
+    };
+    std::vector<int64_t> cand;
+    const int64_t ft = std::max<int64_t>(1, full_tiles);
+    if (forced > 0)
+        cand.push_back(std::min<int64_t>(forced, ft));
+    else
+    {
+        for (int64_t w = 1; w <= std::max<int64_t>(1, wmax); ++w)
+            cand.push_back(std::min<int64_t>(ft, std::max<int64_t>(1, (resident * w) / qtiles)));
+        cand.push_back(ft);
+    }
+    double best = -1.0;
+    for (int64_t sp : cand)
+    {
+        int64_t spl = 0, tps = 0;
+        const double sc = score_of(sp, &spl, &tps);
+        if (sc > best)
+        {
+            best = sc;
+            *splits_out = spl;
+            *tps_out = tps;
+        }
+    }
+    return best;
+}
+
+extern "C" int nn_b200_plan_splits(int64_t qtiles, int64_t full_tiles, int64_t resident_ctas, int64_t max_waves,
+                                   int64_t *splits, int64_t *tiles_per_split)
+{
+    if (qtiles < 1 || full_tiles < 0 || resident_ctas < 1 || !splits || !tiles_per_split)
+        return fail(NN_B200_EINVAL, "bad plan_splits arguments");
+    plan_splits(qtiles, full_tiles, resident_ctas, max_waves, 0, splits, tiles_per_split);
+    return NN_B200_OK;
+}
+
 static int make_plan(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan *p)
 {
     int variant = (int)g_opt.variant.load();
@@ -282,52 +341,21 @@ static int make_plan(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan 
             // tile-shape factor from the B200 sweeps (profiles/): single-query tiles cannot use the
             // pair-packed math, 2-query tiles pay more shared-memory loads per pair when k is small
             const double f_q = q == 1 ? 0.85 : (q == 2 && k < 8 ? 0.95 : 1.0);
-            auto score_of = [&](int64_t sp, int64_t *tps_out) {
-                const int64_t tps = full_tiles > 0 ? (full_tiles + sp - 1) / sp : 0;
-                const int64_t spl = full_tiles > 0 ? (full_tiles + tps - 1) / tps : 1;
-                const int64_t total = spl * qtiles;
-                double e_fill;
-                if (total >= resident)
-                {
-                    const int64_t waves = (total + resident - 1) / resident;
-                    e_fill = (double)total / (double)(waves * resident);
-                }
-                else // fewer CTAs than slots: the FMA pipe needs the full occupancy to stay busy
-                    e_fill = std::pow((double)total / (double)resident, 0.7);
-                const double e_amort = tps > 0 ? (double)tps / ((double)tps + 0.1) : 1.0;
-                *tps_out = tps;
-                return e_pad * e_fill * e_amort * f_q;
-            };
-            std::vector<int64_t> sc;
-            if (forced_splits > 0)
-                sc.push_back(std::min<int64_t>(forced_splits, std::max<int64_t>(1, full_tiles)));
-            else
+            int64_t spl = 1, tps = 0;
+            const double sco = e_pad * f_q * plan_splits(qtiles, full_tiles, resident, g_opt.waves.load(), forced_splits,
+                                                         &spl, &tps);
+            if (sco > best_score)
             {
-                const int64_t wmax = std::max<int64_t>(1, g_opt.waves.load());
-                for (int64_t w = 1; w <= wmax; ++w)
-                    sc.push_back(std::min<int64_t>(std::max<int64_t>(1, full_tiles),
-                                                   std::max<int64_t>(1, (resident * w) / qtiles)));
-                sc.push_back(std::max<int64_t>(1, full_tiles));
-            }
-            for (int64_t sp : sc)
-            {
-                int64_t tps = 0;
-                // tiny, bounded preference for more CTAs at equal score (dynamic scheduling evens out
-                // variance between SMs)
-                const double sco = score_of(sp, &tps) + 1e-4 * std::min(1.0, (double)(sp * qtiles) / (8.0 * resident));
-                if (sco > best_score)
-                {
-                    best_score = sco;
-                    p->q = qs;
-                    p->scalar = math;
-                    p->tile_q = tq;
-                    p->tile_r = tr;
-                    p->occ = occ;
-                    p->regs = li.regs;
-                    p->qtiles = (uint32_t)qtiles;
-                    p->tiles_per_split = (uint32_t)tps;
-                    p->splits = full_tiles > 0 ? (uint32_t)((full_tiles + tps - 1) / tps) : 1u;
-                }
+                best_score = sco;
+                p->q = qs;
+                p->scalar = math;
+                p->tile_q = tq;
+                p->tile_r = tr;
+                p->occ = occ;
+                p->regs = li.regs;
+                p->qtiles = (uint32_t)qtiles;
+                p->tiles_per_split = (uint32_t)tps;
+                p->splits = (uint32_t)spl;
             }
             if (forced_q)
                 break;

@@ -26,7 +26,7 @@ _i32p = ctypes.POINTER(ctypes.c_int)
 _u64p = ctypes.POINTER(ctypes.c_uint64)
 
 
-def build(ref: bool = True, ref_gpu: bool = False) -> None:
+def build(ref: bool = True, ref_gpu: bool = False, harness: bool = False) -> None:
     """Compile liboracle.so and, when /root/reference is present, oracle/_ref."""
     targets = ["all"]
     if os.path.isdir("/root/reference/sources/src"):
@@ -34,6 +34,8 @@ def build(ref: bool = True, ref_gpu: bool = False) -> None:
             targets.append("ref")
         if ref_gpu:
             targets.append("ref_gpu")
+        if harness:
+            targets.append("harness")
     subprocess.run(["make", "-s", "-C", _HERE] + targets, check=True)
 
 

@@ -108,3 +108,24 @@ def test_product_never_references_the_oracle():
                     if re.search(r"(import\s+oracle|from\s+oracle|oracle/|liboracle|libref_|nn_oracle)", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_launch_planner_fills_the_gpu_without_shredding_the_work(nn):
+    """The split planner (pure arithmetic) at the five BASELINE shapes on a 148-SM part: the grid is
+    at least one full wave when the work allows it, a whole number of waves within 3%, and never
+    more than 8 waves of CTAs (a tie-break bug once produced one CTA per reference tile)."""
+    import ctypes
+    L = nn.lib()
+    # (query tiles, full reference tiles, resident CTAs): tile shapes of nn_kernels.cuh at occupancy 4
+    shapes = {"cfg1 k3": (4, 96, 148 * 9), "cfg2 k16": (8, 8192, 592), "cfg4 k16": (128, 131072, 592),
+              "cfg5 k3": (1024, 1542, 592), "tiny": (1, 0, 592), "one tile": (3, 1, 592)}
+    for name, (qt, ft, res) in shapes.items():
+        sp, tps = ctypes.c_int64(), ctypes.c_int64()
+        assert L.nn_b200_plan_splits(qt, ft, res, 8, ctypes.byref(sp), ctypes.byref(tps)) == 0
+        total = sp.value * qt
+        assert sp.value >= 1 and sp.value * tps.value >= ft, name
+        assert (sp.value - 1) * tps.value < max(ft, 1), name          # no empty split
+        assert total <= 8 * res + qt, (name, total)
+        if ft * qt >= res:                                            # enough work for a full wave
+            waves = -(-total // res)
+            assert total >= res and total / (waves * res) > 0.97, (name, total)

@@ -243,3 +243,22 @@ def test_multi_gpu_host_entry(nn, oracle):
     # same through the reference's own entry point, all GPUs
     S, R = oracle.ta_sample(7)
     assert nn.cudaCallback(16, 1024, 65536, S, R).tolist() == TA["indices"][7]
+
+
+def test_reference_harness_runs_unmodified_against_the_library(nn):
+    """oracle/_ref/harness_main = the reference's TA harness (main.cu, generator.h, utils.h, compiled
+    unmodified from /root/reference by oracle/Makefile) + the reference's own v0 as Callback1 + THIS
+    library as Callback10 through integration/core.h.  Its own checker (main.cu:84-97) must report
+    0 errors on all eight samples, i.e. the output of the reference's screen.log for Callback10."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "harness_main")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/harness_main not built (needs /root/reference at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    txt = out.stdout
+    assert "on running CALLBACK10" in txt
+    errs = [l for l in txt.splitlines() if l.startswith("errors/total")]
+    assert len(errs) == 8 and all(l.split(":")[1].strip().startswith("0/") for l in errs), txt[-1500:]
+    shapes = [l.split(",")[1:4] for l in txt.splitlines() if l.startswith("Callback2,")]
+    assert [[int(x) for x in s] for s in shapes] == TA["samples"]
