@@ -922,8 +922,12 @@ extern "C" void nn_b200_cudaCallback(int k, int m, int n, float *searchPoints, f
     *results = tmp;
 }
 
-// The reference's C++-linkage entry point (core.h:71, core.cu:1282-1297).
+// The reference's C++-linkage entry point (core.h:71, core.cu:1282-1297).  Build with
+// -DNN_B200_NO_CXX_ENTRY when the host program keeps its own ::cudaCallback that forwards to
+// nn_b200_cudaCallback (variant b).
+#ifndef NN_B200_NO_CXX_ENTRY
 void cudaCallback(int k, int m, int n, float *searchPoints, float *referencePoints, int **results)
 {
     nn_b200_cudaCallback(k, m, n, searchPoints, referencePoints, results);
 }
+#endif
