@@ -129,11 +129,12 @@ NN_B200_API int nn_b200_probe_fp32(int mode, int iters, double *lane_ops_per_s);
  * grid); written into buf (NUL-terminated, truncated to len). */
 NN_B200_API int nn_b200_describe_plan(int k, int m, int64_t n, char *buf, size_t len);
 
-/* Introspection of the launch planner (pure arithmetic, no device needed): for `qtiles` query tiles,
- * `full_tiles` whole reference tiles and a GPU that holds `resident_ctas` CTAs at once, how many
- * reference splits per query tile the query-register kernel is launched with. */
-NN_B200_API int nn_b200_plan_splits(int64_t qtiles, int64_t full_tiles, int64_t resident_ctas, int64_t max_waves,
-                                    int64_t *splits, int64_t *tiles_per_split);
+/* Introspection of the launch planner (pure arithmetic, no device needed): for the query-register
+ * kernel with `q` queries per thread (tile = 128 q queries) at `occ` CTAs per SM on `sms` SMs, how
+ * many reference splits per query tile a search of m queries x n references is launched with and
+ * how many references each split covers (a multiple of 4). */
+NN_B200_API int nn_b200_plan_splits(int k, int q, int occ, int sms, int64_t m, int64_t n, int64_t *splits,
+                                    int64_t *refs_per_split);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -58,7 +58,7 @@ static int fail(int code, const char *fmt, ...)
 
 struct Options
 {
-    std::atomic<int64_t> variant{0};         // 0 auto, 1 qreg, 2 rreg, 3 plain
+    std::atomic<int64_t> variant{0};         // 0 auto, 1 qreg, 2 rreg, 3 plain, 4 rtma
     std::atomic<int64_t> splits{0};          // qreg reference splits per query tile (0 auto)
     std::atomic<int64_t> qreg_q{0};          // qreg queries per thread (0 auto)
     std::atomic<int64_t> math{2};            // 2 f32x2 over query pairs, 1 f32x2 over dims, 0 scalar (A/B only)
@@ -68,6 +68,7 @@ struct Options
     std::atomic<int64_t> waves{8};           // qreg: most CTA waves considered
 };
 static Options g_opt;
+static std::atomic<int64_t> g_opt_epoch{0}; // bumped by every set_option: cached plans of older epochs are stale
 
 extern "C" int nn_b200_set_option(const char *name, int64_t value)
 {
@@ -92,6 +93,7 @@ extern "C" int nn_b200_set_option(const char *name, int64_t value)
         g_opt.waves = value;
     else
         return fail(NN_B200_EINVAL, "unknown option '%s'", name);
+    g_opt_epoch++;
     return NN_B200_OK;
 }
 
@@ -146,6 +148,30 @@ static cudaError_t k_query_rreg(int k, int mq, bool soa, LaunchInfo *li, int *rp
 #define X(KK)                                                                                                          \
     case KK:                                                                                                           \
         return query_rreg<KK>(mq, soa, li, rpb);
+        NN_FOR_K(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+static cudaError_t k_launch_rtma(int k, int mq, const RregArgs &a, dim3 grid, cudaStream_t st)
+{
+    switch (k)
+    {
+#define X(KK)                                                                                                          \
+    case KK:                                                                                                           \
+        return launch_rtma<KK>(mq, a, grid, st);
+        NN_FOR_K(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+static cudaError_t k_query_rtma(int k, int mq, LaunchInfo *li, int *tile_refs)
+{
+    switch (k)
+    {
+#define X(KK)                                                                                                          \
+    case KK:                                                                                                           \
+        return query_rtma<KK>(mq, li, tile_refs);
         NN_FOR_K(X)
 #undef X
     }
@@ -232,76 +258,94 @@ static int dev_info(int dev, DevInfo *out)
 // ---------------------------------------------------------------------------------------------
 struct Plan
 {
-    int variant = 0; // 1 qreg, 2 rreg, 3 plain
+    int variant = 0; // 1 qreg, 2 rreg, 3 plain, 4 rtma
+    int tile_refs = 0; // rtma
     // qreg
     int q = 0, scalar = 0, tile_q = 0, tile_r = 0, occ = 0, regs = 0;
-    uint32_t qtiles = 0, splits = 0, tiles_per_split = 0;
+    uint32_t qtiles = 0, splits = 0, refs_per_split = 0;
     // rreg
     int rreg_ctas = 0;
     // plain
     uint32_t plain_splits = 1;
 };
 
-// Pure part of the query-register plan: how many reference splits a query tile gets.  Inputs:
-// query tiles, full reference tiles, CTAs the GPU holds at once (SMs x occupancy), most waves
-// considered.  Returns the efficiency estimate (SM fill / wave quantisation x per-split prologue
-// amortisation) of the best candidate and writes its split count and tiles per split.
-static double plan_splits(int64_t qtiles, int64_t full_tiles, int64_t resident, int64_t wmax, int64_t forced,
-                          int64_t *splits_out, int64_t *tps_out)
+// Time model of the query-register kernel (pure arithmetic, SM clock cycles) for `splits` reference
+// splits per query tile.  A CTA is four warps, one per SM sub-partition, so c co-resident CTAs put
+// c warps on every FMA pipe; a warp needs (q/2)(3k-1) packed instructions of 2 pipe cycles per
+// reference.  eff(c) is the measured fraction of the pipe that c warps keep busy (one warp alone
+// exposes its shared-memory and dependent-issue latencies), ovh the per-CTA prologue (query loads,
+// first TMA tile) and epilogue (index resolution, atomics).
+static double qreg_model_cycles(int k, int q, int occ, int sms, int64_t m, int64_t n, int64_t splits, int64_t *rps_out)
 {
-    auto score_of = [&](int64_t sp, int64_t *spl_out, int64_t *tps) {
-        *tps = full_tiles > 0 ? (full_tiles + sp - 1) / sp : 0;
-        const int64_t spl = full_tiles > 0 ? (full_tiles + *tps - 1) / *tps : 1;
-        const int64_t total = spl * qtiles;
-        double e_fill;
-        if (total >= resident)
-        {
-            const int64_t waves = (total + resident - 1) / resident;
-            e_fill = (double)total / (double)(waves * resident);
-        }
-        else // fewer CTAs than slots: the FMA pipe needs the full occupancy to stay busy
-            e_fill = std::pow((double)total / (double)resident, 0.7);
-        const double e_amort = *tps > 0 ? (double)*tps / ((double)*tps + 0.1) : 1.0;
-        *spl_out = spl;
-        // tiny, bounded preference for more CTAs at equal score (dynamic scheduling evens out
-        // variance between SMs)
-        return e_fill * e_amort + 1e-4 * std::min(1.0, (double)total / (8.0 * (double)resident));
-    };
+    const int64_t qtiles = (m + 128 * (int64_t)q - 1) / (128 * (int64_t)q);
+    const int64_t total = qtiles * splits;
+    int64_t rps = (n + splits - 1) / splits;
+    rps = (rps + 3) / 4 * 4;
+    if (rps_out)
+        *rps_out = rps;
+    // f_q: measured pipe share of the tile shape itself (shared loads and compares per packed
+    // instruction grow as the tile narrows; one query per thread cannot use the pair-packed math)
+    const double f_q = q >= 8 ? 1.0 : (q >= 4 ? 0.988 : (q >= 2 ? 0.965 : 1.0 / 1.3));
+    const double cpr = (q >= 2 ? (q / 2) * (3.0 * k - 1.0) * 2.0 : (3.0 * k - 1.0)) / f_q;
+    auto eff = [](int64_t c) { return c <= 1 ? 0.58 : (c == 2 ? 0.78 : (c == 3 ? 0.86 : 0.92)); };
+    const double ovh = 5000.0 + 600.0 * q;
+    const int64_t slots = (int64_t)sms * occ;
+    const int64_t full_waves = total / slots, rem = total % slots;
+    double t = (double)full_waves * (ovh + (double)occ * (double)rps * cpr / eff(occ));
+    if (rem)
+    {
+        const int64_t c = (rem + sms - 1) / sms;
+        t += ovh + (double)c * (double)rps * cpr / eff(c);
+    }
+    return t;
+}
+
+// Best split count for one tile shape: candidates are the counts that fill the SMs evenly -- c CTAs
+// on every SM for c = 1..occ, or w whole waves of SMs x occ CTAs -- never fewer than 32 references
+// per split.  Returns the modelled cycles.
+static double plan_splits(int k, int q, int occ, int sms, int64_t m, int64_t n, int64_t wmax, int64_t forced,
+                          int64_t *splits_out, int64_t *rps_out)
+{
+    const int64_t qtiles = (m + 128 * (int64_t)q - 1) / (128 * (int64_t)q);
+    const int64_t smax = std::max<int64_t>(1, n / 32);
     std::vector<int64_t> cand;
-    const int64_t ft = std::max<int64_t>(1, full_tiles);
     if (forced > 0)
-        cand.push_back(std::min<int64_t>(forced, ft));
+        cand.push_back(std::min(forced, smax));
     else
     {
-        for (int64_t w = 1; w <= std::max<int64_t>(1, wmax); ++w)
-            cand.push_back(std::min<int64_t>(ft, std::max<int64_t>(1, (resident * w) / qtiles)));
-        cand.push_back(ft);
+        cand.push_back(1);
+        for (int64_t c = 1; c <= occ; ++c)
+            cand.push_back(((int64_t)sms * c) / qtiles);
+        for (int64_t w = 2; w <= std::max<int64_t>(1, wmax); ++w)
+            cand.push_back(((int64_t)sms * occ * w) / qtiles);
     }
     double best = -1.0;
     for (int64_t sp : cand)
     {
-        int64_t spl = 0, tps = 0;
-        const double sc = score_of(sp, &spl, &tps);
-        if (sc > best)
+        sp = std::max<int64_t>(1, std::min(sp, smax));
+        int64_t rps = 0;
+        const double t = qreg_model_cycles(k, q, occ, sms, m, n, sp, &rps);
+        const int64_t used = (n + rps - 1) / rps; // splits that actually receive references
+        if (best < 0 || t < best * 0.999)
         {
-            best = sc;
-            *splits_out = spl;
-            *tps_out = tps;
+            best = t;
+            *splits_out = std::max<int64_t>(1, used);
+            *rps_out = rps;
         }
     }
     return best;
 }
 
-extern "C" int nn_b200_plan_splits(int64_t qtiles, int64_t full_tiles, int64_t resident_ctas, int64_t max_waves,
-                                   int64_t *splits, int64_t *tiles_per_split)
+extern "C" int nn_b200_plan_splits(int k, int q, int occ, int sms, int64_t m, int64_t n, int64_t *splits,
+                                   int64_t *refs_per_split)
 {
-    if (qtiles < 1 || full_tiles < 0 || resident_ctas < 1 || !splits || !tiles_per_split)
+    if (k < NN_B200_KMIN || k > NN_B200_KMAX || q < 1 || occ < 1 || sms < 1 || m < 1 || n < 1 || !splits || !refs_per_split)
         return fail(NN_B200_EINVAL, "bad plan_splits arguments");
-    plan_splits(qtiles, full_tiles, resident_ctas, max_waves, 0, splits, tiles_per_split);
+    plan_splits(k, q, occ, sms, m, n, 8, 0, splits, refs_per_split);
     return NN_B200_OK;
 }
 
-static int make_plan(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan *p)
+static int make_plan_uncached(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan *p)
 {
     int variant = (int)g_opt.variant.load();
     if (soa)
@@ -335,18 +379,11 @@ static int make_plan(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan 
             const int q = tq / 128;
             const int occ = li.occ > 0 ? li.occ : 1;
             const int64_t qtiles = ((int64_t)m + tq - 1) / tq;
-            const int64_t full_tiles = n / tr;
-            const int64_t resident = (int64_t)di.sms * occ;
-            const double e_pad = (double)m / (double)(qtiles * tq);
-            // tile-shape factor from the B200 sweeps (profiles/): single-query tiles cannot use the
-            // pair-packed math, 2-query tiles pay more shared-memory loads per pair when k is small
-            const double f_q = q == 1 ? 0.85 : (q == 2 && k < 8 ? 0.95 : 1.0);
-            int64_t spl = 1, tps = 0;
-            const double sco = e_pad * f_q * plan_splits(qtiles, full_tiles, resident, g_opt.waves.load(), forced_splits,
-                                                         &spl, &tps);
-            if (sco > best_score)
+            int64_t spl = 1, rps = 0;
+            const double cyc = plan_splits(k, q, occ, di.sms, m, n, g_opt.waves.load(), forced_splits, &spl, &rps);
+            if (best_score < 0 || cyc < best_score)
             {
-                best_score = sco;
+                best_score = cyc;
                 p->q = qs;
                 p->scalar = math;
                 p->tile_q = tq;
@@ -354,7 +391,7 @@ static int make_plan(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan 
                 p->occ = occ;
                 p->regs = li.regs;
                 p->qtiles = (uint32_t)qtiles;
-                p->tiles_per_split = (uint32_t)tps;
+                p->refs_per_split = (uint32_t)rps;
                 p->splits = (uint32_t)spl;
             }
             if (forced_q)
@@ -377,6 +414,23 @@ static int make_plan(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan 
         p->regs = li.regs;
         p->rreg_ctas = di.sms * per_sm;
     }
+    else if (variant == 4)
+    {
+        LaunchInfo li{};
+        int tr = 0;
+        cudaError_t e = k_query_rtma(k, 8, &li, &tr);
+        if (e != cudaSuccess)
+            return fail(NN_B200_ECUDA, "reference-stream kernel query failed for k=%d: %s", k, cudaGetErrorString(e));
+        int per_sm = (int)g_opt.rreg_ctas_per_sm.load();
+        if (per_sm <= 0)
+            per_sm = li.occ > 0 ? li.occ : 1;
+        p->occ = per_sm;
+        p->regs = li.regs;
+        p->tile_refs = tr;
+        // persistent grid, but never more CTAs than full tiles (+1 so that the ragged end has an owner)
+        const int64_t tiles = n / tr + 1;
+        p->rreg_ctas = (int)std::min<int64_t>((int64_t)di.sms * per_sm, tiles);
+    }
     else if (variant == 3)
     {
         const int64_t qblocks = ((int64_t)m + 127) / 128;
@@ -386,6 +440,43 @@ static int make_plan(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan 
     }
     else
         return fail(NN_B200_EINVAL, "unknown variant %d", variant);
+    return NN_B200_OK;
+}
+
+// Planning asks the runtime for register counts and occupancies of several candidate kernels; that
+// costs tens of microseconds on the host, more than a small search takes on the device.  Plans are
+// therefore remembered per (device, shape, option epoch).
+struct PlanKey
+{
+    int dev, k, m, soa;
+    int64_t n, epoch;
+    bool operator==(const PlanKey &o) const
+    {
+        return dev == o.dev && k == o.k && m == o.m && soa == o.soa && n == o.n && epoch == o.epoch;
+    }
+};
+static std::mutex g_plan_mu;
+static std::vector<std::pair<PlanKey, Plan>> g_plans;
+
+static int make_plan(int dev, int k, int m, int64_t n, bool soa, const DevInfo &di, Plan *p)
+{
+    const PlanKey key{dev, k, m, soa ? 1 : 0, n, g_opt_epoch.load()};
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        for (size_t i = 0; i < g_plans.size(); ++i)
+            if (g_plans[i].first == key)
+            {
+                *p = g_plans[i].second;
+                return NN_B200_OK;
+            }
+    }
+    const int rc = make_plan_uncached(k, m, n, soa, di, p);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    if (g_plans.size() >= 64)
+        g_plans.erase(g_plans.begin());
+    g_plans.emplace_back(key, *p);
     return NN_B200_OK;
 }
 
@@ -421,7 +512,7 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
     if (rc)
         return rc;
     Plan p;
-    rc = make_plan(k, m, n, soa, di, &p);
+    rc = make_plan(dev, k, m, n, soa, di, &p);
     if (rc)
         return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -435,15 +526,16 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
         a.n = (uint32_t)n;
         a.index_base = index_base;
         a.splits = p.splits;
-        a.tiles_per_split = p.tiles_per_split;
+        a.refs_per_split = p.refs_per_split;
         a.keys = keys;
         a.neg_zero = -0.0f;
         CU(k_launch_qreg(k, p.q, p.scalar, a, p.qtiles, st));
         g_launches++;
     }
-    else if (p.variant == 2)
+    else if (p.variant == 2 || p.variant == 4)
     {
         // full passes of 8 queries, then one pass with the smallest even width covering the tail
+        const bool rtma = p.variant == 4;
         auto launch = [&](int q0, int count, int mq) -> int {
             int done = 0;
             const int passes = (count + mq - 1) / mq;
@@ -458,7 +550,10 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
                 a.index_base = index_base;
                 a.keys = keys + q0 + done * mq;
                 a.neg_zero = -0.0f;
-                CU(k_launch_rreg(k, mq, soa, a, dim3((unsigned)p.rreg_ctas, (unsigned)py), st));
+                if (rtma)
+                    CU(k_launch_rtma(k, mq, a, dim3((unsigned)p.rreg_ctas, (unsigned)py), st));
+                else
+                    CU(k_launch_rreg(k, mq, soa, a, dim3((unsigned)p.rreg_ctas, (unsigned)py), st));
                 g_launches++;
                 done += py;
             }
@@ -510,17 +605,20 @@ extern "C" int nn_b200_describe_plan(int k, int m, int64_t n, char *buf, size_t 
     if (rc)
         return rc;
     Plan p;
-    rc = make_plan(k, m, n, false, di, &p);
+    rc = make_plan(dev, k, m, n, false, di, &p);
     if (rc)
         return rc;
     if (p.variant == 1)
         snprintf(buf, len,
-                 "qreg k=%d Q=%d %s tile=%dq x %dr regs=%d occ=%d qtiles=%u splits=%u tiles/split=%u ctas=%u sms=%d", k,
+                 "qreg k=%d Q=%d %s tile=%dq x %dr regs=%d occ=%d qtiles=%u splits=%u refs/split=%u ctas=%u sms=%d", k,
                  p.q, p.scalar == 0 ? "scalar" : (p.scalar == 1 ? "f32x2-dims" : "f32x2-pairs"), p.tile_q, p.tile_r, p.regs, p.occ, p.qtiles, p.splits,
-                 p.tiles_per_split, p.qtiles * p.splits, di.sms);
+                 p.refs_per_split, p.qtiles * p.splits, di.sms);
     else if (p.variant == 2)
         snprintf(buf, len, "rreg k=%d f32x2-pairs regs=%d ctas/sm=%d ctas=%d passes8=%d tail=%d sms=%d", k, p.regs,
                  p.occ, p.rreg_ctas, m / 8, m % 8, di.sms);
+    else if (p.variant == 4)
+        snprintf(buf, len, "rtma k=%d f32x2-pairs regs=%d ctas/sm=%d ctas=%d tile=%dr passes8=%d tail=%d sms=%d", k,
+                 p.regs, p.occ, p.rreg_ctas, p.tile_refs, m / 8, m % 8, di.sms);
     else
         snprintf(buf, len, "plain k=%d splits=%u sms=%d", k, p.plain_splits, di.sms);
     return NN_B200_OK;

@@ -33,6 +33,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "nn_launch.h"
 
 // build-time tuning knobs (overridable with -D for A/B builds; defaults are the measured best)
@@ -50,6 +52,12 @@
 #endif
 #ifndef NN_RREG_L2PF
 #define NN_RREG_L2PF 0 // slot-batches ahead that a CTA asks the L2 to prefetch (0 = off; no gain measured)
+#endif
+#ifndef NN_RTMA_PIPELINE
+#define NN_RTMA_PIPELINE 1 // reference-stream kernel: software-pipeline the shared loads over half tiles
+#endif
+#ifndef NN_QREG_PREFETCH
+#define NN_QREG_PREFETCH 1 // query-register kernel: load the next reference group while computing the current one
 #endif
 #ifndef NN_QREG_REGCAP_LOW
 #define NN_QREG_REGCAP_LOW 0 // 1: always compile the query-register kernel for 4 CTAs/SM (128 regs)
@@ -238,12 +246,30 @@ struct QregCfg
     static constexpr int STAGES = 3;
     static constexpr int TILE_FLOATS = TR * K;
     static constexpr uint32_t TILE_BYTES = TILE_FLOATS * 4u;
-    static constexpr size_t SMEM = (size_t)STAGES * TILE_BYTES + 64;
+    // ring + barriers + slack: the software-pipelined chunk loop reads one reference group (at most
+    // 240 bytes) past the end of the tile it is working on; the value is never used
+    static constexpr size_t SMEM = (size_t)STAGES * TILE_BYTES + 64 + 256;
 };
 
+// Software pipelining of the shared-memory loads pays in the narrow tiles (Q <= 4) that small
+// query counts use: few warps per scheduler, short chunks, so the load latency at the head of every
+// chunk is exposed (ncu at k=3, m=1024, n=65536: FMA pipe 66% -> 75% of active cycles).  The wide
+// tiles keep their registers for queries (measured: -1% at Q = 8).  It needs one more reference
+// group of registers under the 128-register cap.
 template <int K, int Q, int MATH>
+struct QregPrefetch
+{
+    static constexpr bool value =
+        NN_QREG_PREFETCH && Q <= 4 && (Q * K + 2 * Geo<K>::G * K + (MATH == 2 ? 52 : 36) <= 128);
+};
+
+// One chunk of CH references against the thread's Q queries; cm[] receives the chunk minima.
+// PF: `nxt` holds the chunk's first reference group on entry (loaded while the previous chunk was
+// computed) and the first group of the FOLLOWING chunk on exit, so no shared-memory latency sits
+// between two chunks.
+template <int K, int Q, int MATH, bool PF>
 __device__ __forceinline__ void qreg_chunk(const float *__restrict__ sm, const float (&q)[Q][K], float (&cm)[Q],
-                                           const float2 nz)
+                                           const float2 nz, float4 (&nxt)[Geo<K>::F4])
 {
     constexpr int G = Geo<K>::G, F4 = Geo<K>::F4, CH = QregCfg<K>::CH;
     float hold[Q];
@@ -251,15 +277,33 @@ __device__ __forceinline__ void qreg_chunk(const float *__restrict__ sm, const f
     for (int g0 = 0; g0 < CH; g0 += G)
     {
         float grp[G * K];
-        const float4 *p4 = reinterpret_cast<const float4 *>(sm + g0 * K);
-#pragma unroll
-        for (int i = 0; i < F4; ++i)
+        if constexpr (PF)
         {
-            const float4 v = p4[i];
-            grp[4 * i + 0] = v.x;
-            grp[4 * i + 1] = v.y;
-            grp[4 * i + 2] = v.z;
-            grp[4 * i + 3] = v.w;
+#pragma unroll
+            for (int i = 0; i < F4; ++i)
+            {
+                grp[4 * i + 0] = nxt[i].x;
+                grp[4 * i + 1] = nxt[i].y;
+                grp[4 * i + 2] = nxt[i].z;
+                grp[4 * i + 3] = nxt[i].w;
+            }
+            const float4 *n4 = reinterpret_cast<const float4 *>(sm + (g0 + G) * K);
+#pragma unroll
+            for (int i = 0; i < F4; ++i)
+                nxt[i] = n4[i];
+        }
+        else
+        {
+            const float4 *p4 = reinterpret_cast<const float4 *>(sm + g0 * K);
+#pragma unroll
+            for (int i = 0; i < F4; ++i)
+            {
+                const float4 v = p4[i];
+                grp[4 * i + 0] = v.x;
+                grp[4 * i + 1] = v.y;
+                grp[4 * i + 2] = v.z;
+                grp[4 * i + 3] = v.w;
+            }
         }
 #pragma unroll
         for (int g = 0; g < G; ++g)
@@ -314,6 +358,7 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
 {
     using C = QregCfg<K>;
     constexpr int CH = C::CH, TR = C::TR, STAGES = C::STAGES;
+    constexpr bool PF = QregPrefetch<K, Q, MATH>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tiles = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);
@@ -321,13 +366,35 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
     const int tid = threadIdx.x;
     const uint32_t split = blockIdx.x % a.splits;
     const uint32_t qtile = blockIdx.x / a.splits;
-    const uint32_t full_tiles = a.n / TR;
-    const uint32_t rem = a.n - full_tiles * TR;
-    const uint32_t t0 = min(split * a.tiles_per_split, full_tiles);
-    const uint32_t t1 = min(t0 + a.tiles_per_split, full_tiles);
-    const bool tail = (rem != 0) && (split == a.splits - 1);
-    if (t0 >= t1 && !tail)
+    // This CTA's references: [r0, r1).  r0 is a multiple of CH (= 4 points, 16-byte aligned for every
+    // k); whole chunks [r0, r1c) stream through the TMA ring in tiles of up to TR points, and the
+    // ragged end of the reference set (< CH points, last split only) is handled after the loop.
+    const uint32_t r0 = min(split * a.refs_per_split, a.n);
+    const uint32_t r1 = (split == a.splits - 1) ? a.n : min(r0 + a.refs_per_split, a.n);
+    const uint32_t r1c = r0 + ((r1 - r0) / CH) * CH;
+    const uint32_t ntiles = (r1c - r0 + TR - 1) / TR;
+    if (r1 <= r0)
         return;
+
+    auto issue = [&](uint32_t t, uint32_t stage) { // tile t of this CTA -> ring stage
+        const uint32_t first = r0 + t * TR;
+        const uint32_t bytes = min((uint32_t)TR, r1c - first) * (uint32_t)(K * 4);
+        mbar_expect_tx(&full[stage], bytes);
+        bulk_g2s(tiles + (size_t)stage * C::TILE_FLOATS, a.R + (size_t)first * K, bytes, &full[stage]);
+    };
+    // The first reference tiles are requested before anything else so that their HBM latency
+    // overlaps the query loads (only thread 0 touches the barriers before the CTA-wide sync).
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            mbar_init(&full[s], 1);
+        mbar_fence_init();
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s)
+            if ((uint32_t)s < ntiles)
+                issue(s, s);
+    }
 
     // this thread's queries (clamped so that out-of-range slots compute on a valid row)
     float q[Q][K];
@@ -346,51 +413,30 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
         best[j] = __int_as_float(0x7f800000);
         bref[j] = NO_REF;
     }
-
-    if (tid == 0)
-    {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s)
-            mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
     __syncthreads();
 
-    if (tid == 0)
-    {
-#pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s)
-            if (t0 + s < t1)
-            {
-                mbar_expect_tx(&full[s], C::TILE_BYTES);
-                bulk_g2s(tiles + (size_t)s * C::TILE_FLOATS, a.R + (size_t)(t0 + s) * C::TILE_FLOATS, C::TILE_BYTES,
-                         &full[s]);
-            }
-    }
-
     uint32_t stage = 0, parity = 0;
-    for (uint32_t t = t0; t < t1; ++t)
+    for (uint32_t t = 0; t < ntiles; ++t)
     {
         __syncthreads(); // everyone is done with tile t-1: its stage may be refilled
-        if (tid == 0)
-        {
-            const uint32_t tn = t + STAGES - 1;
-            if (tn < t1)
-            {
-                const uint32_t sn = (stage + STAGES - 1) % STAGES;
-                mbar_expect_tx(&full[sn], C::TILE_BYTES);
-                bulk_g2s(tiles + (size_t)sn * C::TILE_FLOATS, a.R + (size_t)tn * C::TILE_FLOATS, C::TILE_BYTES,
-                         &full[sn]);
-            }
-        }
+        if (tid == 0 && t + STAGES - 1 < ntiles)
+            issue(t + STAGES - 1, (stage + STAGES - 1) % STAGES);
         mbar_wait(&full[stage], parity);
         const float *sm = tiles + (size_t)stage * C::TILE_FLOATS;
-        const uint32_t ref0 = t * TR;
+        const uint32_t ref0 = r0 + t * TR;
+        const int cnt = (int)min((uint32_t)TR, r1c - ref0);
+        float4 nxt[Geo<K>::F4];
+        if constexpr (PF)
+        {
+#pragma unroll
+            for (int i = 0; i < Geo<K>::F4; ++i)
+                nxt[i] = reinterpret_cast<const float4 *>(sm)[i];
+        }
 #pragma unroll kQregUnroll
-        for (int c = 0; c < TR; c += CH)
+        for (int c = 0; c < cnt; c += CH)
         {
             float cm[Q];
-            qreg_chunk<K, Q, MATH>(sm + c * K, q, cm, nz);
+            qreg_chunk<K, Q, MATH, PF>(sm + c * K, q, cm, nz, nxt);
 #pragma unroll
             for (int j = 0; j < Q; ++j)
                 if (cm[j] < best[j])
@@ -406,28 +452,26 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
         }
     }
 
-    if (tail)
+    if (r1c < r1)
     {
-        // last, partial tile: plain cooperative loads; slots past n are NaN (a NaN distance never wins)
+        // ragged end of the reference set (1..CH-1 points): plain loads; the chunk is padded with NaN
+        // (a NaN distance never wins)
         __syncthreads();
-        const uint32_t ref0 = full_tiles * TR;
-        const uint32_t padded = ((rem + CH - 1) / CH) * CH;
-        const float *src = a.R + (size_t)ref0 * K;
-        for (uint32_t i = tid; i < padded * K; i += NT)
-            tiles[i] = (i < rem * K) ? __ldg(src + i) : __int_as_float(0x7fffffff);
+        const float *src = a.R + (size_t)r1c * K;
+        const uint32_t have = (r1 - r1c) * K;
+        for (uint32_t i = tid; i < (uint32_t)(CH * K); i += NT)
+            tiles[i] = (i < have) ? __ldg(src + i) : __int_as_float(0x7fffffff);
         __syncthreads();
-        for (uint32_t c = 0; c < padded; c += CH)
-        {
-            float cm[Q];
-            qreg_chunk<K, Q, MATH>(tiles + c * K, q, cm, nz);
+        float cm[Q];
+        float4 unused[Geo<K>::F4];
+        qreg_chunk<K, Q, MATH, false>(tiles, q, cm, nz, unused);
 #pragma unroll
-            for (int j = 0; j < Q; ++j)
-                if (cm[j] < best[j])
-                {
-                    best[j] = cm[j];
-                    bref[j] = ref0 + c;
-                }
-        }
+        for (int j = 0; j < Q; ++j)
+            if (cm[j] < best[j])
+            {
+                best[j] = cm[j];
+                bref[j] = r1c;
+            }
     }
 
     // resolve the exact (lowest) index inside the winning chunk, then fold into the global keys
@@ -690,6 +734,403 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
                             if (d2 == best[j])
                                 idx = r;
                         }
+                    }
+                }
+            }
+            key = pack_key(best[j], a.index_base + idx);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        if (lane == 0 && j < valid_q && key < (KEY_INIT | NO_REF))
+            atomicMin(a.keys + q0 + j, key);
+    }
+}
+
+// =============================================================================================
+// Kernel C -- "reference-stream" kernel: the few-query case with the HBM stream decoupled from the
+// register file.
+//
+// Same roles as kernel B (thread <-> its own references, query pairs broadcast from shared memory,
+// all-packed f32x2 math), but the references reach the SM through a STAGES-deep shared-memory ring
+// filled by the TMA unit: a producer warp issues one cp.async.bulk per tile (TILE_BYTES contiguous
+// bytes of the native AoS array) signalled on a `full` mbarrier; each of the NW consumer warps
+// copies ITS references of the tile from shared memory into registers (128-bit LDS), releases the
+// stage at once on the `empty` mbarrier and only then does the arithmetic.  So the bytes in flight
+// per SM are (STAGES-1) x TILE_BYTES x CTAs/SM regardless of the register budget, HBM is read in
+// large fully-used bursts, and no warp ever waits on a global load inside the math.
+// (ncu on kernel B at k = 8, m = 8: 27% more DRAM sectors than the reference set holds, FMA pipe
+// 63% active with long-scoreboard the top stall -- profiles/r01_ncu_summary.txt.)
+// Tile t of the reference set goes to CTA t % gridDim.x (persistent grid); the ragged end of the set
+// (n % TILE_REFS references) is read with plain loads by the CTA whose turn it is.
+// =============================================================================================
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+template <int K, int PT, int NW, int STAGES>
+struct RtmaCfg
+{
+    static constexpr int G = Geo<K>::G;
+    static constexpr int NTC = NW * 32;              // consumer threads
+    static constexpr int TILE_REFS = NTC * PT * G;   // references per tile
+    static constexpr int TILE_FLOATS = TILE_REFS * K;
+    static constexpr uint32_t TILE_BYTES = TILE_FLOATS * 4u;
+    static constexpr size_t smem(int mq) { return (size_t)STAGES * TILE_BYTES + (size_t)STAGES * 16 + (size_t)(mq / 2) * K * 8; }
+};
+
+template <int K, int MQ, int PT, int NW, int STAGES, int MINB>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const RregArgs a)
+{
+    static_assert(MQ % 2 == 0, "queries are processed in pairs");
+    using C = RtmaCfg<K, PT, NW, STAGES>;
+    constexpr int G = C::G, F4 = Geo<K>::F4, P = G * PT, NP = MQ / 2, NTC = C::NTC;
+    constexpr uint32_t TILE_REFS = C::TILE_REFS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *ring = reinterpret_cast<float *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);
+    uint64_t *empty = full + STAGES;
+    float2 *sq = reinterpret_cast<float2 *>(empty + STAGES); // sq[pair*K + d] = (qa_d, qb_d)
+
+    const int tid = threadIdx.x;
+    const int pass = blockIdx.y;
+    const int q0 = pass * MQ;
+    const int valid_q = min(MQ, a.mq_total - q0); // >= 1
+    for (int i = tid; i < NP * K; i += (NW + 1) * 32)
+    {
+        const int pr = i / K, d = i % K;
+        const int qa = min(2 * pr, valid_q - 1), qb = min(2 * pr + 1, valid_q - 1);
+        sq[i] = make_float2(__ldg(a.S + (size_t)(q0 + qa) * K + d), __ldg(a.S + (size_t)(q0 + qb) * K + d));
+    }
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+        {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const uint32_t nfull = a.n / TILE_REFS;
+    const uint32_t rem = a.n - nfull * TILE_REFS;
+    const uint32_t mine = blockIdx.x < nfull ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool tail = rem != 0 && blockIdx.x == nfull % gridDim.x;
+
+    if (tid >= NTC)
+    { // ---- producer warp: one elected lane keeps the ring full ----
+        if (tid == NTC)
+        {
+            uint32_t s = 0, ph = 0;
+            for (uint32_t j = 0; j < mine; ++j)
+            {
+                if (j >= (uint32_t)STAGES)
+                    mbar_wait(&empty[s], ph ^ 1); // the stage's previous tile has been copied out by all warps
+                const uint32_t tile = blockIdx.x + j * gridDim.x;
+                mbar_expect_tx(&full[s], C::TILE_BYTES);
+                bulk_g2s(ring + (size_t)s * C::TILE_FLOATS, a.R + (size_t)tile * C::TILE_FLOATS, C::TILE_BYTES, &full[s]);
+                if (++s == (uint32_t)STAGES)
+                {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumer warps ----
+    float best[MQ];
+    uint32_t bref[MQ];
+    const float2 nz = make_float2(a.neg_zero, a.neg_zero);
+#pragma unroll
+    for (int j = 0; j < MQ; ++j)
+    {
+        best[j] = __int_as_float(0x7f800000);
+        bref[j] = NO_REF;
+    }
+    const int lane = tid & 31;
+
+    // minima of this thread's P references against the MQ queries, folded into (best, bref = tile)
+    auto fold_tile = [&](const float(&ref)[P * K], uint32_t tile) {
+#pragma unroll
+        for (int pr = 0; pr < NP; ++pr)
+        {
+            float2 qp[K];
+            if constexpr (K % 2 == 0)
+            {
+                const float4 *q4 = reinterpret_cast<const float4 *>(sq + pr * K);
+#pragma unroll
+                for (int f = 0; f < K / 2; ++f)
+                {
+                    const float4 v = q4[f];
+                    qp[2 * f] = make_float2(v.x, v.y);
+                    qp[2 * f + 1] = make_float2(v.z, v.w);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int d = 0; d < K; ++d)
+                    qp[d] = sq[pr * K + d];
+            }
+            float2 rm = make_float2(0.f, 0.f), hold = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+            {
+                const float2 d = sqdist_pair<K>(qp, &ref[p * K], nz);
+                if (p == 0 && P > 1)
+                    hold = d;
+                else if (p == 0)
+                    rm = d;
+                else if (p == 1)
+                    rm = make_float2(fminf(hold.x, d.x), fminf(hold.y, d.y));
+                else if ((p & 1) == 0 && p + 1 < P)
+                    hold = d;
+                else if ((p & 1) == 1)
+                    rm = make_float2(fminf(fminf(rm.x, hold.x), d.x), fminf(fminf(rm.y, hold.y), d.y));
+                else
+                    rm = make_float2(fminf(rm.x, d.x), fminf(rm.y, d.y));
+            }
+            if (rm.x < best[2 * pr])
+            {
+                best[2 * pr] = rm.x;
+                bref[2 * pr] = tile;
+            }
+            if (rm.y < best[2 * pr + 1])
+            {
+                best[2 * pr + 1] = rm.y;
+                bref[2 * pr + 1] = tile;
+            }
+        }
+    };
+
+    if constexpr (PT % 2 == 0 && NN_RTMA_PIPELINE)
+    {
+        // Software pipeline over HALF tiles: while the arithmetic of one half runs, the 128-bit shared
+        // loads of the next half (the second half of this tile, or the first half of the next tile
+        // when it has already landed) are in flight, so neither the shared-memory latency nor the
+        // wait for the TMA sits on the warp's critical path.
+        constexpr int HT = PT / 2, HP = P / 2;
+        float refA[HP * K], refB[HP * K];
+        auto lds_half = [&](float(&dst)[HP * K], uint32_t st, int half) {
+            const float4 *t4 = reinterpret_cast<const float4 *>(ring + (size_t)st * C::TILE_FLOATS);
+#pragma unroll
+            for (int i = 0; i < HT; ++i)
+            {
+                const float4 *p4 = t4 + (size_t)((half * HT + i) * NTC + tid) * F4;
+#pragma unroll
+                for (int f = 0; f < F4; ++f)
+                {
+                    const float4 v = p4[f];
+                    dst[i * G * K + 4 * f + 0] = v.x;
+                    dst[i * G * K + 4 * f + 1] = v.y;
+                    dst[i * G * K + 4 * f + 2] = v.z;
+                    dst[i * G * K + 4 * f + 3] = v.w;
+                }
+            }
+        };
+        // minima of HP references against the MQ queries, folded into rm[] (FIRST: rm is unset)
+        auto fold_half = [&](const float(&ref)[HP * K], float2(&rm)[NP], const bool FIRST) {
+#pragma unroll
+            for (int pr = 0; pr < NP; ++pr)
+            {
+                float2 qp[K];
+                if constexpr (K % 2 == 0)
+                {
+                    const float4 *q4 = reinterpret_cast<const float4 *>(sq + pr * K);
+#pragma unroll
+                    for (int f = 0; f < K / 2; ++f)
+                    {
+                        const float4 v = q4[f];
+                        qp[2 * f] = make_float2(v.x, v.y);
+                        qp[2 * f + 1] = make_float2(v.z, v.w);
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int d = 0; d < K; ++d)
+                        qp[d] = sq[pr * K + d];
+                }
+                float2 hold = make_float2(0.f, 0.f);
+                bool have = !FIRST;
+#pragma unroll
+                for (int p = 0; p < HP; ++p)
+                {
+                    const float2 d = sqdist_pair<K>(qp, &ref[p * K], nz);
+                    if ((p & 1) == 0 && p + 1 < HP)
+                        hold = d;
+                    else if ((p & 1) == 1)
+                    {
+                        rm[pr] = have ? make_float2(fminf(fminf(rm[pr].x, hold.x), d.x), fminf(fminf(rm[pr].y, hold.y), d.y))
+                                      : make_float2(fminf(hold.x, d.x), fminf(hold.y, d.y));
+                        have = true;
+                    }
+                    else
+                    {
+                        rm[pr] = have ? make_float2(fminf(rm[pr].x, d.x), fminf(rm[pr].y, d.y)) : d;
+                        have = true;
+                    }
+                }
+            }
+        };
+        uint32_t s = 0, ph = 0;
+        if (mine > 0)
+        {
+            mbar_wait(&full[0], 0);
+            lds_half(refA, 0, 0);
+        }
+        for (uint32_t j = 0; j < mine; ++j)
+        {
+            lds_half(refB, s, 1);
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&empty[s]); // every shared load of this tile by this warp precedes the (release) arrive
+            float2 rm[NP];
+            fold_half(refA, rm, true);
+            uint32_t s2 = s + 1, ph2 = ph;
+            if (s2 == (uint32_t)STAGES)
+            {
+                s2 = 0;
+                ph2 ^= 1;
+            }
+            const bool more = j + 1 < mine;
+            bool ready = false;
+            if (more)
+            {
+                ready = __all_sync(0xffffffffu, mbar_test(&full[s2], ph2));
+                if (ready)
+                    lds_half(refA, s2, 0);
+            }
+            fold_half(refB, rm, false);
+            const uint32_t tile = blockIdx.x + j * gridDim.x;
+#pragma unroll
+            for (int pr = 0; pr < NP; ++pr)
+            {
+                if (rm[pr].x < best[2 * pr])
+                {
+                    best[2 * pr] = rm[pr].x;
+                    bref[2 * pr] = tile;
+                }
+                if (rm[pr].y < best[2 * pr + 1])
+                {
+                    best[2 * pr + 1] = rm[pr].y;
+                    bref[2 * pr + 1] = tile;
+                }
+            }
+            if (more && !ready)
+            {
+                mbar_wait(&full[s2], ph2);
+                lds_half(refA, s2, 0);
+            }
+            s = s2;
+            ph = ph2;
+        }
+    }
+    else
+    {
+        uint32_t s = 0, ph = 0;
+        for (uint32_t j = 0; j < mine; ++j)
+        {
+            mbar_wait(&full[s], ph);
+            float ref[P * K];
+            const float4 *t4 = reinterpret_cast<const float4 *>(ring + (size_t)s * C::TILE_FLOATS);
+#pragma unroll
+            for (int i = 0; i < PT; ++i)
+            {
+                const float4 *p4 = t4 + (size_t)(i * NTC + tid) * F4;
+#pragma unroll
+                for (int f = 0; f < F4; ++f)
+                {
+                    const float4 v = p4[f];
+                    ref[i * G * K + 4 * f + 0] = v.x;
+                    ref[i * G * K + 4 * f + 1] = v.y;
+                    ref[i * G * K + 4 * f + 2] = v.z;
+                    ref[i * G * K + 4 * f + 3] = v.w;
+                }
+            }
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&empty[s]); // this warp's copy is in registers: the stage may be refilled
+            fold_tile(ref, blockIdx.x + j * gridDim.x);
+            if (++s == (uint32_t)STAGES)
+            {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    }
+    if (tail)
+    { // ragged end of the reference set: plain loads, slots past n are NaN (a NaN distance never wins)
+        float ref[P * K];
+        const size_t f0 = (size_t)nfull * C::TILE_FLOATS, fend = (size_t)a.n * K;
+#pragma unroll
+        for (int i = 0; i < PT; ++i)
+#pragma unroll
+            for (int e = 0; e < G * K; ++e)
+            {
+                const size_t f = f0 + (size_t)(i * NTC + tid) * (G * K) + e;
+                ref[i * G * K + e] = f < fend ? __ldg(a.R + f) : __int_as_float(0x7fffffff);
+            }
+        fold_tile(ref, nfull);
+    }
+
+    // Warp-level merge, as in kernel B: only lanes that hold the warp minimum resolve their exact
+    // (lowest) index by re-reading their references of the winning tile.
+#pragma unroll
+    for (int j = 0; j < MQ; ++j)
+    {
+        float wmin = best[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+        unsigned long long key = KEY_INIT | NO_REF;
+        if (bref[j] != NO_REF && best[j] == wmin)
+        {
+            float qv[K];
+#pragma unroll
+            for (int d = 0; d < K; ++d)
+                qv[d] = (j & 1) ? sq[(j / 2) * K + d].y : sq[(j / 2) * K + d].x;
+            uint32_t idx = 0;
+#pragma unroll
+            for (int i = PT - 1; i >= 0; --i)
+            {
+#pragma unroll
+                for (int g = G - 1; g >= 0; --g)
+                {
+                    const uint32_t r = bref[j] * TILE_REFS + (uint32_t)(i * NTC + tid) * G + g;
+                    if (r < a.n)
+                    {
+                        float rr[K];
+#pragma unroll
+                        for (int d = 0; d < K; ++d)
+                            rr[d] = __ldg(a.R + (size_t)r * K + d);
+                        const float d2 = sqdist<K, 0, false>(qv, rr);
+                        if (d2 == best[j])
+                            idx = r;
                     }
                 }
             }

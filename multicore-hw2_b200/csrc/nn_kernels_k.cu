@@ -191,6 +191,101 @@ cudaError_t query_rreg<NN_K>(int mq, bool soa, LaunchInfo *info, int *refs_per_b
     NN_RREG_DISPATCH(query_rreg_one, info, refs_per_batch)
 }
 
+// ---- reference-stream kernel (TMA ring) ----------------------------------------------------------
+#ifndef NN_RTMA_NW
+#define NN_RTMA_NW 8 // consumer warps per CTA (one more warp produces)
+#endif
+#ifndef NN_RTMA_STAGES
+#define NN_RTMA_STAGES 3
+#endif
+#ifndef NN_RTMA_MINB
+#define NN_RTMA_MINB 2 // CTAs per SM the register budget is compiled for
+#endif
+#ifndef NN_RTMA_SLOT_FLOATS
+#define NN_RTMA_SLOT_FLOATS 32 // reference floats per thread per tile
+#endif
+template <int K>
+struct RtmaSel
+{
+    static constexpr int NW = NN_RTMA_NW, STAGES = NN_RTMA_STAGES, MINB = NN_RTMA_MINB;
+    static constexpr int PT = (NN_RTMA_SLOT_FLOATS / (Geo<K>::G * K)) >= 1 ? (NN_RTMA_SLOT_FLOATS / (Geo<K>::G * K)) : 1;
+    using Cfg = RtmaCfg<K, PT, NW, STAGES>;
+};
+
+template <int K, int MQ>
+static cudaError_t launch_rtma_one(const RregArgs &a, dim3 grid, cudaStream_t st)
+{
+    using S = RtmaSel<K>;
+    if ((a.mq_total + MQ - 1) / MQ != (int)grid.y || a.mq_total < 1)
+        return cudaErrorInvalidValue;
+    auto kern = nn_rtma_kernel<K, MQ, S::PT, S::NW, S::STAGES, S::MINB>;
+    static bool configured = false;
+    if (!configured)
+    {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::Cfg::smem(MQ));
+        if (e != cudaSuccess)
+            return e;
+        configured = true;
+    }
+    kern<<<grid, (S::NW + 1) * 32, S::Cfg::smem(MQ), st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int K, int MQ>
+static cudaError_t query_rtma_one(LaunchInfo *info, int *tile_refs)
+{
+    using S = RtmaSel<K>;
+    auto kern = nn_rtma_kernel<K, MQ, S::PT, S::NW, S::STAGES, S::MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::Cfg::smem(MQ));
+    if (e != cudaSuccess)
+        return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess)
+        return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (S::NW + 1) * 32, S::Cfg::smem(MQ));
+    if (e != cudaSuccess)
+        return e;
+    info->regs = fa.numRegs;
+    info->smem = (int)S::Cfg::smem(MQ);
+    info->occ = occ;
+    *tile_refs = S::Cfg::TILE_REFS;
+    return cudaSuccess;
+}
+
+template <>
+cudaError_t launch_rtma<NN_K>(int mq, const RregArgs &a, dim3 grid, cudaStream_t st)
+{
+    switch (mq)
+    {
+    case 2:
+        return launch_rtma_one<NN_K, 2>(a, grid, st);
+    case 4:
+        return launch_rtma_one<NN_K, 4>(a, grid, st);
+    case 8:
+        return launch_rtma_one<NN_K, 8>(a, grid, st);
+    default:
+        return cudaErrorInvalidValue;
+    }
+}
+
+template <>
+cudaError_t query_rtma<NN_K>(int mq, LaunchInfo *info, int *tile_refs)
+{
+    switch (mq)
+    {
+    case 2:
+        return query_rtma_one<NN_K, 2>(info, tile_refs);
+    case 4:
+        return query_rtma_one<NN_K, 4>(info, tile_refs);
+    case 8:
+        return query_rtma_one<NN_K, 8>(info, tile_refs);
+    default:
+        return cudaErrorInvalidValue;
+    }
+}
+
 template <>
 cudaError_t launch_plain<NN_K>(const float *S, const float *R, int m, uint32_t n, uint32_t index_base, uint32_t splits,
                                unsigned long long *keys, cudaStream_t st)

@@ -16,7 +16,7 @@ struct QregArgs
     uint32_t n;
     uint32_t index_base;
     uint32_t splits;          // reference splits per query tile
-    uint32_t tiles_per_split; // full tiles per split
+    uint32_t refs_per_split;  // references per split (multiple of 4; the last split takes what is left)
     unsigned long long *keys;
     float neg_zero;           // must be -0.0f: run-time addend of the exact fma(d, d, -0) square
 };
@@ -48,6 +48,10 @@ template <int K>
 cudaError_t launch_rreg(int mq, bool soa, const RregArgs &a, dim3 grid, cudaStream_t st);
 template <int K>
 cudaError_t query_rreg(int mq, bool soa, LaunchInfo *info, int *refs_per_batch);
+template <int K>
+cudaError_t launch_rtma(int mq, const RregArgs &a, dim3 grid, cudaStream_t st);
+template <int K>
+cudaError_t query_rtma(int mq, LaunchInfo *info, int *tile_refs);
 template <int K>
 cudaError_t launch_plain(const float *S, const float *R, int m, uint32_t n, uint32_t index_base, uint32_t splits,
                          unsigned long long *keys, cudaStream_t st);

@@ -54,7 +54,7 @@ def test_no_contracted_multiply_add_in_device_code(nn):
         n = {o: ops.count(o) for o in ("FFMA", "FFMA2", "FADD2", "FMUL2")}
         assert n["FFMA"] == 0, name
         mq = re.search(r"nn_qreg_kernelILi(\d+)ELi\d+ELi\d+ELi2E", name)
-        mr = re.search(r"nn_rreg_kernelILi(\d+)E", name)
+        mr = re.search(r"nn_r(?:reg|tma)_kernelILi(\d+)E", name)
         if mq or mr:
             k = int((mq or mr).group(1))
             seen_pair_kernels += 1
@@ -111,21 +111,28 @@ def test_product_never_references_the_oracle():
 
 
 def test_launch_planner_fills_the_gpu_without_shredding_the_work(nn):
-    """The split planner (pure arithmetic) at the five BASELINE shapes on a 148-SM part: the grid is
-    at least one full wave when the work allows it, a whole number of waves within 3%, and never
+    """The split planner (pure arithmetic) at the five BASELINE shapes on a 148-SM part, with the
+    tile shapes and occupancies of nn_kernels.cuh: every split is a whole number of 4-reference
+    chunks, the splits cover the reference set exactly once, the grid fills the SMs evenly (a
+    whole number of CTAs per SM, or whole waves within 3%), and the work is never shredded into
     more than 8 waves of CTAs (a tie-break bug once produced one CTA per reference tile)."""
     import ctypes
     L = nn.lib()
-    # (query tiles, full reference tiles, resident CTAs): tile shapes of nn_kernels.cuh at occupancy 4
-    shapes = {"cfg1 k3": (4, 96, 148 * 9), "cfg2 k16": (8, 8192, 592), "cfg4 k16": (128, 131072, 592),
-              "cfg5 k3": (1024, 1542, 592), "tiny": (1, 0, 592), "one tile": (3, 1, 592)}
-    for name, (qt, ft, res) in shapes.items():
-        sp, tps = ctypes.c_int64(), ctypes.c_int64()
-        assert L.nn_b200_plan_splits(qt, ft, res, 8, ctypes.byref(sp), ctypes.byref(tps)) == 0
-        total = sp.value * qt
-        assert sp.value >= 1 and sp.value * tps.value >= ft, name
-        assert (sp.value - 1) * tps.value < max(ft, 1), name          # no empty split
-        assert total <= 8 * res + qt, (name, total)
-        if ft * qt >= res:                                            # enough work for a full wave
-            waves = -(-total // res)
-            assert total >= res and total / (waves * res) > 0.97, (name, total)
+    sms = 148
+    # name: (k, queries/thread, CTAs/SM, m, n)
+    shapes = {"cfg1 k3 q2": (3, 2, 9, 1024, 65536), "cfg1 k3 q4": (3, 4, 8, 1024, 65536),
+              "cfg2 k16": (16, 4, 4, 4096, 1 << 20), "cfg4 k16": (16, 4, 4, 65536, 1 << 24),
+              "cfg5 k3": (3, 8, 4, 1 << 20, 1 << 20), "tiny": (3, 1, 9, 1, 5), "one chunk": (8, 8, 4, 300, 4)}
+    for name, (k, q, occ, m, n) in shapes.items():
+        sp, rps = ctypes.c_int64(), ctypes.c_int64()
+        assert L.nn_b200_plan_splits(k, q, occ, sms, m, n, ctypes.byref(sp), ctypes.byref(rps)) == 0
+        qtiles = -(-m // (128 * q))
+        total = sp.value * qtiles
+        assert sp.value >= 1 and rps.value % 4 == 0 and rps.value >= 4, name
+        assert sp.value * rps.value >= n > (sp.value - 1) * rps.value, (name, sp.value, rps.value)  # exact cover
+        assert total <= 8 * sms * occ + qtiles, (name, total)
+        if n * qtiles >= 64 * sms * occ:                              # enough work for a full grid
+            per_sm = total / sms
+            waves = -(-total // (sms * occ))
+            even = abs(per_sm - round(per_sm)) < 0.03 * per_sm or total / (waves * sms * occ) > 0.97
+            assert total >= sms and even, (name, total)

@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TA = json.load(open(os.path.join(GOLD, "ta_results.json")))
 REF = json.load(open(os.path.join(GOLD, "ref_v0_cases.json")))
 
-VARIANTS = {"auto": 0, "qreg": 1, "rreg": 2, "plain": 3}
+VARIANTS = {"auto": 0, "qreg": 1, "rreg": 2, "plain": 3, "rtma": 4}
 
 
 @pytest.fixture(scope="module")
@@ -53,7 +53,7 @@ def gpu_keys(nn, S, R, variant="auto", soa=False, index_base=0, q=0, math=2):
         nn.set_option("math", 2)
 
 
-@pytest.mark.parametrize("variant", ["auto", "qreg", "rreg", "plain"])
+@pytest.mark.parametrize("variant", ["auto", "qreg", "rreg", "plain", "rtma"])
 @pytest.mark.parametrize("case", REF["cases"], ids=lambda c: f"{c['kind']}-k{c['k']}-m{c['m']}-n{c['n']}")
 def test_reference_v0_fixture(nn, oracle, case, variant):
     """Indices equal the reference's own v0 outputs (fixture); keys equal the oracle's."""
@@ -102,6 +102,16 @@ def test_shards_and_chunks_fold_to_the_same_keys(nn, oracle, k):
                 device.nearest_keys(dS, dR[b:b + c], keys, b)
         assert np.array_equal(keys.cpu().numpy().view(np.uint64), want)
         assert np.array_equal(device.keys_unpack(keys).cpu().numpy(), (want & 0xFFFFFFFF).astype(np.int32))
+
+
+@pytest.mark.parametrize("variant", ["rreg", "rtma"])
+@pytest.mark.parametrize("k,m,n", [(8, 8, 300007), (3, 7, 250001), (16, 13, 120000), (5, 1, 199999), (12, 2, 65536)])
+def test_few_query_kernels_over_many_tiles(nn, oracle, variant, k, m, n):
+    """The two few-query kernels on reference sets that span many tiles and every CTA of the
+    persistent grid, with duplicated references (lowest index must win across tiles, warps and
+    CTAs) and a ragged end; bit-exact keys against the oracle."""
+    S, R = cases.make("duplicated", 5100 + k + m, k, m, n)
+    assert np.array_equal(gpu_keys(nn, S, R, variant), oracle.keys(S, R))
 
 
 @pytest.mark.parametrize("k,n", [(3, 10007), (7, 4096), (8, 5001), (16, 3000), (13, 1)])
