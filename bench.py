@@ -256,7 +256,15 @@ def main():
     assert shard.count == n_local and begin == rank * n_local
     keys = device.new_keys(m, dev)
     out = torch.empty(m, dtype=torch.int32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # L2 flush between steps: 256 MiB written, then another 256 MiB read, so that the 126 MB L2 holds
+    # neither the previous step's references nor dirty lines whose write-back would ride on the
+    # timed kernel's HBM stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
+
+    def l2_flush():
+        flush.zero_()
+        flush_rd.sum()
 
     def step():
         device.keys_init(keys)
@@ -277,7 +285,7 @@ def main():
     launches0 = nn.launch_count()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
-        flush.zero_()  # L2 flush, outside the per-step event window
+        l2_flush()  # outside the per-step event window
         ev[i][0].record()
         device.keys_init(keys)
         kev[i][0].record()
@@ -305,21 +313,39 @@ def main():
     value = pairs_per_step / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (this rank's fused distance+argmin launch) --------------
+    # north_star: the slower of 3k non-fused FP32 lane-ops per pair at the FP32 issue peak and
+    # n*k*4 reference bytes at HBM bandwidth.
     kern_ms_avg = sum(kern_ms) / len(kern_ms)
+    kern_s = kern_ms_avg * 1e-3
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     ops = 3.0 * k * m * n_local
-    achieved = ops / (kern_ms_avg * 1e-3)
-    nominal = sms * 128 * peaks["sm_max_mhz"] * 1e6
-    line_roof = {
-        "bound": "fp32", "kernel": "nn_qreg_kernel" if m > 48 else "nn_rreg_kernel",
-        "achieved": achieved / 1e12, "peak": nominal / 1e12, "unit": "TFLOP/s (non-fused FP32 lane-ops: 3k per pair)",
-        "frac": achieved / nominal,
-        "peak_source": f"{sms} SMs x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
-        "kernel_ms": kern_ms_avg,
-        "hbm": {"achieved_gbs": n_local * k * 4 / (kern_ms_avg * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
-                "frac": n_local * k * 4 / (kern_ms_avg * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-        "traffic": None,
-    }
+    ref_bytes = float(n_local) * k * 4
+    fp32_peak = sms * 128 * peaks["sm_max_mhz"] * 1e6
+    hbm_peak = peaks["hbm_gbs"] * 1e9
+    t_fp32, t_hbm = ops / fp32_peak, ref_bytes / hbm_peak
+    plan = nn.describe_plan(k, m, n_local)
+    kernel_name = {"qreg": "nn_qreg_kernel", "rreg": "nn_rreg_kernel", "rtma": "nn_rtma_kernel"}.get(plan.split()[0], plan.split()[0])
+    fp32_part = {"achieved_tlops": ops / kern_s / 1e12, "peak_tlops": fp32_peak / 1e12, "frac": t_fp32 / kern_s,
+                 "bound_ms": t_fp32 * 1e3,
+                 "peak_source": f"{sms} SMs x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)"}
+    hbm_part = {"achieved_gbs": ref_bytes / kern_s / 1e9, "peak_gbs": peaks["hbm_gbs"], "frac": t_hbm / kern_s,
+                "bound_ms": t_hbm * 1e3, "peak_source": f"{peaks['source']} hbm_gbs (measured copy bandwidth)"}
+    if t_fp32 >= t_hbm:
+        line_roof = {"bound": "fp32", "kernel": kernel_name, "achieved": fp32_part["achieved_tlops"],
+                     "peak": fp32_part["peak_tlops"], "unit": "TFLOP/s (non-fused FP32 lane-ops: 3k per pair)",
+                     "frac": fp32_part["frac"]}
+    else:
+        line_roof = {"bound": "hbm", "kernel": kernel_name, "achieved": hbm_part["achieved_gbs"],
+                     "peak": hbm_part["peak_gbs"], "unit": "GB/s", "frac": hbm_part["frac"]}
+    line_roof.update({"kernel_ms": kern_ms_avg, "fp32": fp32_part, "hbm": hbm_part,
+                      "algorithmic": {"lane_ops_per_launch": ops, "bytes_per_launch": ref_bytes},
+                      "traffic": None})
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(args.workload)
+        if t and t.get("kernel") == kernel_name:
+            line_roof["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+            line_roof["traffic_source"] = t["source"]
     if rank == 0:
         try:
             meas = nn.probe_fp32(0)
@@ -327,7 +353,7 @@ def main():
             line_roof["peak_measured"] = max(meas, meas2) / 1e12
             line_roof["peak_measured_scalar"] = meas / 1e12
             line_roof["peak_measured_f32x2"] = meas2 / 1e12
-            line_roof["frac_of_measured"] = achieved / max(meas, meas2)
+            line_roof["frac_of_measured"] = (ops / kern_s) / max(meas, meas2)
         except Exception as e:  # measurement aid only
             line_roof["peak_measured_error"] = str(e)
 
@@ -385,8 +411,8 @@ def main():
             "config": {"workload": DESCR[args.workload] + (f"; {world} shards, n_total={n_total}" if world > 1 else ""),
                        "k": k, "m": m, "n_per_gpu": n_local, "n_total": n_total,
                        "parallelism": f"reference shards x{world}, NCCL all-reduce(min) of uint64 keys" if world > 1 else "1 GPU",
-                       "l2": "flushed between steps (256 MiB memset outside the event window)",
-                       "plan": nn.describe_plan(k, m, n_local), "uniform [0,1) float32": True},
+                       "l2": "flushed between steps (256 MiB written then 256 MiB read, outside the event window)",
+                       "plan": plan, "uniform [0,1) float32": True},
             "roofline": line_roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "step_ms_min_max": [min(step_ms), max(step_ms)],

@@ -62,7 +62,7 @@ struct Options
     std::atomic<int64_t> splits{0};          // qreg reference splits per query tile (0 auto)
     std::atomic<int64_t> qreg_q{0};          // qreg queries per thread (0 auto)
     std::atomic<int64_t> math{2};            // 2 f32x2 over query pairs, 1 f32x2 over dims, 0 scalar (A/B only)
-    std::atomic<int64_t> rreg_max_m{48};     // m <= this -> reference-register kernel
+    std::atomic<int64_t> rreg_max_m{112};    // m <= this -> few-query kernels (rreg up to 4 queries, rtma above)
     std::atomic<int64_t> rreg_ctas_per_sm{0}; // 0: occupancy
     std::atomic<int64_t> h2d_chunk_bytes{16 << 20};
     std::atomic<int64_t> waves{8};           // qreg: most CTA waves considered
@@ -350,8 +350,12 @@ static int make_plan_uncached(int k, int m, int64_t n, bool soa, const DevInfo &
     int variant = (int)g_opt.variant.load();
     if (soa)
         variant = 2;
+    // Few queries: every thread streams its own references (roles swapped).  Up to 4 queries the
+    // search is purely HBM-bound and plain register loads stream fastest (6.9 TB/s); from 5 queries
+    // on the FP32 pipe matters as well and the TMA-ring kernel wins at every k (B200 sweeps in
+    // profiles/); beyond ~112 queries the query-register kernel's 128-query tile is full enough.
     if (variant == 0)
-        variant = (m <= g_opt.rreg_max_m.load()) ? 2 : 1;
+        variant = (m <= 4) ? 2 : ((m <= g_opt.rreg_max_m.load()) ? 4 : 1);
     p->variant = variant;
     if (variant == 1)
     {

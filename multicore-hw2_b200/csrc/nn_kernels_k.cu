@@ -192,14 +192,17 @@ cudaError_t query_rreg<NN_K>(int mq, bool soa, LaunchInfo *info, int *refs_per_b
 }
 
 // ---- reference-stream kernel (TMA ring) ----------------------------------------------------------
+// One CTA per SM: 12 consumer warps + 1 producer warp, ring of up to 4 tiles in ~200 KB of shared
+// memory (measured at k = 8, m = 8, n = 2^26 on B200: 0.41 ms, against 0.43-0.44 ms for two CTAs of
+// 8+1 warps per SM and 0.42 ms for 16+1 warps).
 #ifndef NN_RTMA_NW
-#define NN_RTMA_NW 8 // consumer warps per CTA (one more warp produces)
+#define NN_RTMA_NW 12 // consumer warps per CTA (one more warp produces)
 #endif
 #ifndef NN_RTMA_STAGES
-#define NN_RTMA_STAGES 3
+#define NN_RTMA_STAGES 4 // at most; fewer when a tile is large (odd k: 4-point groups)
 #endif
 #ifndef NN_RTMA_MINB
-#define NN_RTMA_MINB 2 // CTAs per SM the register budget is compiled for
+#define NN_RTMA_MINB 1 // CTAs per SM the register budget is compiled for
 #endif
 #ifndef NN_RTMA_SLOT_FLOATS
 #define NN_RTMA_SLOT_FLOATS 32 // reference floats per thread per tile
@@ -207,8 +210,11 @@ cudaError_t query_rreg<NN_K>(int mq, bool soa, LaunchInfo *info, int *refs_per_b
 template <int K>
 struct RtmaSel
 {
-    static constexpr int NW = NN_RTMA_NW, STAGES = NN_RTMA_STAGES, MINB = NN_RTMA_MINB;
+    static constexpr int NW = NN_RTMA_NW, MINB = NN_RTMA_MINB;
     static constexpr int PT = (NN_RTMA_SLOT_FLOATS / (Geo<K>::G * K)) >= 1 ? (NN_RTMA_SLOT_FLOATS / (Geo<K>::G * K)) : 1;
+    static constexpr int TILE_BYTES = NW * 32 * PT * Geo<K>::G * K * 4;
+    static constexpr int FIT = (200 * 1024 / MINB) / TILE_BYTES;
+    static constexpr int STAGES = FIT >= NN_RTMA_STAGES ? NN_RTMA_STAGES : (FIT >= 2 ? FIT : 2);
     using Cfg = RtmaCfg<K, PT, NW, STAGES>;
 };
 
