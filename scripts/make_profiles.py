@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Turns the ncu captures of scripts/gpu_profile.sh (gpurun_out/<tag>_*.ncu-rep) into the committed
+evidence under profiles/: <tag>_ncu_summary.txt (side-by-side metrics + stall reasons),
+<tag>_launches_bench_cfg2.csv (copied) and traffic.json (dram bytes per launch, read by bench.py).
+
+    python scripts/make_profiles.py r01
+"""
+import csv, json, os, shutil, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+caps = ["cfg1_qreg", "cfg2_qreg", "cfg3_rtma", "cfg4s_qreg", "cfg5s_qreg", "m1_rreg", "repack_k16"]
+paths = [os.path.join(ROOT, "gpurun_out", f"{tag}_{c}.ncu-rep") for c in caps]
+paths = [p for p in paths if os.path.exists(p)]
+out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py")] + paths, capture_output=True, text=True).stdout
+hdr = (f"# ncu --set full --clock-control none captures ({tag}), one launch each, nn_bench command lines in scripts/gpu_profile.sh\n"
+       "# cfg4s / cfg5s are 1/16-size slices of configs 4 / 5 (same kernels and tile shapes; the full sizes replay for minutes under ncu)\n")
+open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.txt"), "w").write(hdr + out)
+print(out)
+
+def raw(path):
+    o = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(o.splitlines()))
+    return {h: (v, u) for h, u, v in zip(rows[0], rows[1], rows[2])}
+
+def to_bytes(v, u):
+    x = float(v.replace(",", ""))
+    return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+
+traffic = {}
+for wl, cap, kern, alg in [("cfg1", "cfg1_qreg", "nn_qreg_kernel", 65536 * 3 * 4), ("cfg2", "cfg2_qreg", "nn_qreg_kernel", (1 << 20) * 16 * 4),
+                           ("cfg3", "cfg3_rtma", "nn_rtma_kernel", (1 << 26) * 8 * 4)]:
+    p = os.path.join(ROOT, "gpurun_out", f"{tag}_{cap}.ncu-rep")
+    if not os.path.exists(p):
+        continue
+    d = raw(p)
+    traffic[wl] = {"kernel": kern, "dram_bytes_read": to_bytes(*d["dram__bytes_read.sum"]), "dram_bytes_write": to_bytes(*d["dram__bytes_write.sum"]),
+                   "algorithmic_bytes": alg, "gpu_time_us": float(d["gpu__time_duration.sum"][0].replace(",", "")) * (1e-3 if d["gpu__time_duration.sum"][1] == "ns" else 1.0 if d["gpu__time_duration.sum"][1] == "us" else 1e3),
+                   "source": f"profiles/{tag}_ncu_summary.txt ({tag}_{cap}.ncu-rep, ncu --set full, one launch)"}
+json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+src = os.path.join(ROOT, "gpurun_out", f"{tag}_launches_bench_cfg2.csv")
+if os.path.exists(src):
+    shutil.copy(src, os.path.join(ROOT, "profiles", f"{tag}_launches_bench_cfg2.csv"))
+print(json.dumps(traffic, indent=1))
