@@ -105,7 +105,7 @@ class ClockSampler:
                         self.reasons.add(nme)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.02)
 
     def stop(self):
         self._stop.set()
@@ -211,6 +211,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (contract default): every rank owns the workload's n references; strong: the "
+                         "workload's n references are sharded over the ranks (BASELINE configs[3] at 1/2/4/8 GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -245,15 +248,18 @@ def main():
 
     k, m, n_local = WORKLOADS[args.workload]
     n_total = n_local * world
+    if args.scaling == "strong":
+        n_total = n_local
+        n_local = sharded.ShardedSearch(n_total, rank, world).count
     peaks = measured_peaks()
 
     # ---- inputs: queries replicated, this rank's reference shard; resident in HBM ----------------
     S, _ = make_inputs(k, m, 4, 1000, dev)
     _, R = make_inputs(k, 4, n_local, 2000 + rank, dev)
     shard = sharded.ShardedSearch(n_total, rank, world)
-    # weak scaling keeps the per-rank shard at exactly n_local references
+    # weak scaling keeps the per-rank shard at exactly the workload's n references
     begin = shard.begin
-    assert shard.count == n_local and begin == rank * n_local
+    assert shard.count == n_local and (args.scaling == "strong" or begin == rank * n_local)
     keys = device.new_keys(m, dev)
     out = torch.empty(m, dtype=torch.int32, device=dev)
     # L2 flush between steps: 256 MiB written, then another 256 MiB read, so that the 126 MB L2 holds
@@ -278,10 +284,15 @@ def main():
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    mev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local).start()
+    # clocks are sampled on rank 0 only: NVML queries take driver locks, and with one poller per rank
+    # they delayed launches enough to show up as all-reduce skew (0.20 ms -> 0.05 ms per step at N = 8)
+    sampler = ClockSampler(local if rank == 0 else -1).start()
+    import gc
+    gc.disable()
     launches0 = nn.launch_count()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -292,6 +303,7 @@ def main():
         device.nearest_keys(S, R, keys, begin)
         kev[i][1].record()
         sharded.merge_keys(keys)
+        mev[i].record()
         device.keys_unpack(keys, out)
         ev[i][1].record()
     torch.cuda.synchronize()
@@ -299,11 +311,18 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
+    gc.enable()
     launches = nn.launch_count() - launches0
     clocks = sampler.stop()
 
     step_ms = [a.elapsed_time(b) for a, b in ev]
     kern_ms = [a.elapsed_time(b) for a, b in kev]
+    merge_ms = [kev[i][1].elapsed_time(mev[i]) for i in range(args.steps)]  # incl. waiting for the slowest rank
+    kern_all = torch.tensor([sum(kern_ms) / len(kern_ms)], dtype=torch.float64, device=dev)
+    kern_lo, kern_hi = kern_all.clone(), kern_all.clone()
+    if world > 1:
+        dist.all_reduce(kern_lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(kern_hi, op=dist.ReduceOp.MAX)
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -406,7 +425,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": DESCR[args.workload] + (f"; {world} shards, n_total={n_total}" if world > 1 else ""),
                        "k": k, "m": m, "n_per_gpu": n_local, "n_total": n_total,
@@ -416,6 +435,8 @@ def main():
             "roofline": line_roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "step_ms_min_max": [min(step_ms), max(step_ms)],
+            "merge_ms": sum(merge_ms) / len(merge_ms),
+            "kernel_ms_min_max_over_ranks": [float(kern_lo.item()), float(kern_hi.item())],
         }
         print(json.dumps(line))
     if world > 1:
