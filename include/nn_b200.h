@@ -50,8 +50,10 @@ extern "C" {
  * arrays owned by the caller and only read; *results is allocated with malloc(sizeof(int)*m)
  * and freed by the caller (core.cu:935; main.cu:98).  Synchronous.  Uses every visible GPU
  * (at most n, core.cu:867-868; NN_B200_GPUS=<count> caps it), sharding R contiguously
- * (core.cu:875-883) and merging per-query packed keys with ncclAllReduce(min, u64) instead of
- * the reference's host-side second-level reduce (core.cu:936-957).  On failure it prints
+ * (core.cu:875-883) and merging per-query packed keys on the devices -- every GPU's search kernel
+ * folds into GPU 0's key array with 64-bit system-scope atomicMin over NVLink peer memory, or, where
+ * peer access is unavailable, one ncclAllReduce(min, u64) -- instead of the reference's host-side
+ * second-level reduce (core.cu:936-957).  On failure it prints
  * "Error: ..." and exit(1)s like the reference's CHECK macro (core.h:77-87).
  * The library ALSO exports the C++ symbol `::cudaCallback(int,int,int,float*,float*,int**)`
  * (_Z12cudaCallbackiiiPfS_PPi) with the same body, so the reference's unmodified main.cu links. */
@@ -115,8 +117,10 @@ NN_B200_API int64_t nn_b200_launch_count(void);
 NN_B200_API const char *nn_b200_last_error(void);
 
 /* Tuning knobs for benchmarking/sweeps; production code never needs them.  Known names:
- * "variant" (0 auto, 1 query-register kernel, 2 reference-register kernel, 3 plain kernel),
- * "splits" (0 auto), "h2d_chunk_bytes".  Returns NN_B200_EINVAL for an unknown name. */
+ * "variant" (0 auto, 1 query-register kernel, 2 reference-register kernel, 3 plain kernel, 4 reference-stream kernel),
+ * "splits" (0 auto), "h2d_chunk_bytes", "p2p_merge" (multi-GPU host entry: 1 = the search kernels of
+ * every GPU fold into GPU 0's key array with system-scope atomics over NVLink, 0 = NCCL all-reduce).
+ * Returns NN_B200_EINVAL for an unknown name. */
 NN_B200_API int nn_b200_set_option(const char *name, int64_t value);
 
 /* Measurement aid: sustained rate, in lane-operations per second, at which this device issues

@@ -357,7 +357,10 @@ int main(int argc, char **argv)
             list.push_back(x);
             x.m = 1;
             list.push_back(x);
+            x.variant = 4;
             x.m = 15;
+            list.push_back(x);
+            x.variant = 2;
             x.soa = 1;
             list.push_back(x);
         }

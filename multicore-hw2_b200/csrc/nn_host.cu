@@ -66,6 +66,7 @@ struct Options
     std::atomic<int64_t> rreg_ctas_per_sm{0}; // 0: occupancy
     std::atomic<int64_t> h2d_chunk_bytes{16 << 20};
     std::atomic<int64_t> waves{8};           // qreg: most CTA waves considered
+    std::atomic<int64_t> p2p_merge{1};       // multi-GPU host entry: 1 fold into GPU 0's keys over NVLink, 0 NCCL all-reduce
 };
 static Options g_opt;
 static std::atomic<int64_t> g_opt_epoch{0}; // bumped by every set_option: cached plans of older epochs are stale
@@ -91,6 +92,8 @@ extern "C" int nn_b200_set_option(const char *name, int64_t value)
         g_opt.h2d_chunk_bytes = value;
     else if (s == "waves")
         g_opt.waves = value;
+    else if (s == "p2p_merge")
+        g_opt.p2p_merge = value;
     else
         return fail(NN_B200_EINVAL, "unknown option '%s'", name);
     g_opt_epoch++;
@@ -178,13 +181,13 @@ static cudaError_t k_query_rtma(int k, int mq, LaunchInfo *li, int *tile_refs)
     return cudaErrorInvalidValue;
 }
 static cudaError_t k_launch_plain(int k, const float *S, const float *R, int m, uint32_t n, uint32_t base,
-                                  uint32_t splits, unsigned long long *keys, cudaStream_t st)
+                                  uint32_t splits, unsigned long long *keys, int peer, cudaStream_t st)
 {
     switch (k)
     {
 #define X(KK)                                                                                                          \
     case KK:                                                                                                           \
-        return launch_plain<KK>(S, R, m, n, base, splits, keys, st);
+        return launch_plain<KK>(S, R, m, n, base, splits, keys, peer, st);
         NN_FOR_K(X)
 #undef X
     }
@@ -495,8 +498,10 @@ static int check_shape(int k, int m, int64_t n)
     return NN_B200_OK;
 }
 
+// peer_override: -1 = look at where d_keys lives; 1 = other GPUs fold into the same array
+// concurrently, so even its owner must use system-scope atomics.
 static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const float *d_R, uint32_t index_base,
-                             uint64_t *d_keys, void *stream, bool soa)
+                             uint64_t *d_keys, void *stream, bool soa, int peer_override = -1)
 {
     int rc = check_shape(k, m, n);
     if (rc)
@@ -521,6 +526,16 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
         return rc;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(d_keys);
+    // keys in another GPU's memory (peer-mapped): the kernels fold with system-scope atomics
+    int peer = peer_override > 0 ? 1 : 0;
+    if (peer_override < 0)
+    {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, d_keys) == cudaSuccess)
+            peer = (pa.type == cudaMemoryTypeDevice && pa.device != dev) ? 1 : 0;
+        else
+            (void)cudaGetLastError();
+    }
     if (p.variant == 1)
     {
         QregArgs a;
@@ -533,6 +548,7 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
         a.refs_per_split = p.refs_per_split;
         a.keys = keys;
         a.neg_zero = -0.0f;
+        a.peer_keys = peer;
         CU(k_launch_qreg(k, p.q, p.scalar, a, p.qtiles, st));
         g_launches++;
     }
@@ -554,6 +570,7 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
                 a.index_base = index_base;
                 a.keys = keys + q0 + done * mq;
                 a.neg_zero = -0.0f;
+                a.peer_keys = peer;
                 if (rtma)
                     CU(k_launch_rtma(k, mq, a, dim3((unsigned)p.rreg_ctas, (unsigned)py), st));
                 else
@@ -579,7 +596,7 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
     }
     else
     {
-        CU(k_launch_plain(k, d_S, d_R, m, (uint32_t)n, index_base, p.plain_splits, keys, st));
+        CU(k_launch_plain(k, d_S, d_R, m, (uint32_t)n, index_base, p.plain_splits, keys, peer, st));
         g_launches++;
     }
     return NN_B200_OK;
@@ -786,6 +803,9 @@ struct DevCtx
     size_t capS = 0, capR = 0, capM = 0;
     int *hOut = nullptr; // pinned
     size_t capH = 0;
+    cudaEvent_t done = nullptr; // end of this device's searches (P2P merge)
+    cudaEvent_t keys_ready = nullptr; // device 0: its key array is initialised (P2P merge)
+    int peer_to_0 = -1;         // -1 unknown, 0 no peer access to device 0, 1 enabled
 };
 struct HostCtx
 {
@@ -856,7 +876,10 @@ int ensure_dev(DevCtx &c, int dev, size_t bytesS, size_t bytesR, size_t m, size_
 
 // Enqueue one device's share: queries, its contiguous reference shard in chunks (copy stream)
 // and one search per chunk (compute stream).  Returns without synchronising.
-int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float *R, int64_t begin, int64_t count)
+// `keys0`: non-null = fold into that (peer) key array, already initialised, once `keys_ready` has
+// fired; null = this device's own key array, initialised here.
+int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float *R, int64_t begin, int64_t count,
+                   unsigned long long *keys0, cudaEvent_t keys_ready)
 {
     const size_t bytesS = (size_t)m * k * sizeof(float);
     const size_t bytesR = (size_t)count * k * sizeof(float);
@@ -869,9 +892,15 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
         return rc;
     CU(cudaMemcpyAsync(c.dS, S, bytesS, cudaMemcpyHostToDevice, c.copy));
     CU(cudaEventRecord(c.events[0], c.copy));
-    rc = nn_b200_keys_init(reinterpret_cast<uint64_t *>(c.dKeys), m, c.compute);
-    if (rc)
-        return rc;
+    unsigned long long *keys = keys0 ? keys0 : c.dKeys;
+    if (keys0)
+        CU(cudaStreamWaitEvent(c.compute, keys_ready, 0));
+    else
+    {
+        rc = nn_b200_keys_init(reinterpret_cast<uint64_t *>(c.dKeys), m, c.compute);
+        if (rc)
+            return rc;
+    }
     CU(cudaStreamWaitEvent(c.compute, c.events[0], 0));
     for (size_t ci = 0; ci < nchunks; ++ci)
     {
@@ -881,12 +910,39 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
                            cudaMemcpyHostToDevice, c.copy));
         CU(cudaEventRecord(c.events[ci + 1], c.copy));
         CU(cudaStreamWaitEvent(c.compute, c.events[ci + 1], 0));
-        rc = nn_b200_nearest_keys(k, m, cnt, c.dS, c.dR + (size_t)off * k, (uint32_t)(begin + off),
-                                  reinterpret_cast<uint64_t *>(c.dKeys), c.compute);
+        rc = nearest_keys_impl(k, m, cnt, c.dS, c.dR + (size_t)off * k, (uint32_t)(begin + off),
+                               reinterpret_cast<uint64_t *>(keys), c.compute, false, keys0 ? 1 : 0);
         if (rc)
             return rc;
     }
+    if (!c.done)
+        CU(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+    CU(cudaEventRecord(c.done, c.compute));
     return NN_B200_OK;
+}
+
+// Peer access from every used device to device 0 (whose key array all shards fold into).
+bool ensure_peer_to_0(int gpus)
+{
+    bool all = true;
+    for (int g = 1; g < gpus; ++g)
+    {
+        DevCtx &c = g_ctx.devs[g];
+        if (c.peer_to_0 < 0)
+        {
+            int can = 0;
+            c.peer_to_0 = 0;
+            if (cudaDeviceCanAccessPeer(&can, g, 0) == cudaSuccess && can && cudaSetDevice(g) == cudaSuccess)
+            {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(0, 0);
+                if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled)
+                    c.peer_to_0 = 1;
+            }
+            (void)cudaGetLastError();
+        }
+        all = all && c.peer_to_0 == 1;
+    }
+    return all;
 }
 
 int ensure_comms(int gpus)
@@ -932,12 +988,34 @@ extern "C" int nn_b200_search_host(int k, int m, int n, const float *S, const fl
     if ((int)g_ctx.devs.size() < gpus)
         g_ctx.devs.resize(gpus);
 
+    // Merge of the per-GPU candidates.  Default: every GPU's search kernels fold straight into GPU 0's
+    // key array with system-scope 64-bit atomicMin over NVLink (the exchange step happens inside the
+    // search kernel, tile by tile; GPU 0 only waits for the other GPUs' completion events).  Without
+    // peer access (or with option p2p_merge = 0): one in-place ncclAllReduce(min, uint64).
+    const bool p2p = gpus > 1 && g_opt.p2p_merge.load() != 0 && ensure_peer_to_0(gpus);
+    cudaEvent_t keys_ready = nullptr;
+    if (p2p)
+    {
+        DevCtx &c0 = g_ctx.devs[0];
+        rc = ensure_dev(c0, 0, 16, 16, (size_t)std::max(m, 1), 1);
+        if (rc)
+            return rc;
+        rc = nn_b200_keys_init(reinterpret_cast<uint64_t *>(c0.dKeys), m, c0.compute);
+        if (rc)
+            return rc;
+        if (!c0.keys_ready)
+            CU(cudaEventCreateWithFlags(&c0.keys_ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(c0.keys_ready, c0.compute));
+        keys_ready = c0.keys_ready;
+    }
+    unsigned long long *keys0 = p2p ? g_ctx.devs[0].dKeys : nullptr;
+
     std::vector<int> rcs(gpus, 0);
     std::vector<std::string> errs(gpus);
     auto work = [&](int g) {
         int64_t b = 0, cnt = 0;
         nn_b200_shard_range(n, gpus, g, &b, &cnt);
-        rcs[g] = enqueue_device(g_ctx.devs[g], g, k, m, S, R, b, cnt);
+        rcs[g] = enqueue_device(g_ctx.devs[g], g, k, m, S, R, b, cnt, keys0, keys_ready);
         if (rcs[g])
             errs[g] = t_err;
     };
@@ -967,7 +1045,12 @@ extern "C" int nn_b200_search_host(int k, int m, int n, const float *S, const fl
             return rcs[g];
         }
 
-    if (gpus > 1)
+    if (p2p)
+    {
+        for (int g = 1; g < gpus; ++g)
+            CU(cudaStreamWaitEvent(g_ctx.devs[0].compute, g_ctx.devs[g].done, 0));
+    }
+    else if (gpus > 1)
     {
         rc = ensure_comms(gpus);
         if (rc)

@@ -75,6 +75,18 @@ __device__ __forceinline__ unsigned long long pack_key(float d2, uint32_t idx)
     return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)idx;
 }
 
+// Fold one candidate into a key array.  `peer` != 0: the array lives in ANOTHER GPU's memory (mapped
+// over NVLink by cudaDeviceEnablePeerAccess): the minimum is then a system-scope atomic executed at
+// the owning GPU's L2, which is how the shards of a multi-GPU search merge inside the search kernel
+// itself (replaces the reference's host merge, core.cu:925-957, without a separate collective).
+__device__ __forceinline__ void fold_key(unsigned long long *slot, unsigned long long key, int peer)
+{
+    if (peer)
+        atomicMin_system(slot, key);
+    else
+        atomicMin(slot, key);
+}
+
 // References come in 16-byte-aligned groups of G points (G*K floats = F4 float4) so that every
 // k in 3..16 can be moved with 128-bit accesses from the native AoS layout.
 template <int K>
@@ -493,7 +505,7 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
                         idx = r;
                 }
             }
-            atomicMin(a.keys + qi, pack_key(best[j], a.index_base + idx));
+            fold_key(a.keys + qi, pack_key(best[j], a.index_base + idx), a.peer_keys);
         }
     }
 }
@@ -746,7 +758,7 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
             key = other < key ? other : key;
         }
         if (lane == 0 && j < valid_q && key < (KEY_INIT | NO_REF))
-            atomicMin(a.keys + q0 + j, key);
+            fold_key(a.keys + q0 + j, key, a.peer_keys);
     }
 }
 
@@ -1143,7 +1155,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
             key = other < key ? other : key;
         }
         if (lane == 0 && j < valid_q && key < (KEY_INIT | NO_REF))
-            atomicMin(a.keys + q0 + j, key);
+            fold_key(a.keys + q0 + j, key, a.peer_keys);
     }
 }
 
@@ -1155,7 +1167,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
 template <int K>
 __global__ void __launch_bounds__(128) nn_plain_kernel(const float *__restrict__ S, const float *__restrict__ R, int m,
                                                       uint32_t n, uint32_t index_base, uint32_t refs_per_split,
-                                                      unsigned long long *keys)
+                                                      unsigned long long *keys, int peer_keys)
 {
     const int qi = blockIdx.x * 128 + threadIdx.x;
     if (qi >= m)
@@ -1178,7 +1190,7 @@ __global__ void __launch_bounds__(128) nn_plain_kernel(const float *__restrict__
         }
     }
     if (bidx != NO_REF)
-        atomicMin(keys + qi, pack_key(best, index_base + bidx));
+        fold_key(keys + qi, pack_key(best, index_base + bidx), peer_keys);
 }
 
 // =============================================================================================

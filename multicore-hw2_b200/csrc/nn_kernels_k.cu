@@ -294,13 +294,13 @@ cudaError_t query_rtma<NN_K>(int mq, LaunchInfo *info, int *tile_refs)
 
 template <>
 cudaError_t launch_plain<NN_K>(const float *S, const float *R, int m, uint32_t n, uint32_t index_base, uint32_t splits,
-                               unsigned long long *keys, cudaStream_t st)
+                               unsigned long long *keys, int peer_keys, cudaStream_t st)
 {
     if (splits < 1)
         splits = 1;
     const uint32_t per = (n + splits - 1) / splits;
     dim3 grid((m + 127) / 128, splits);
-    nn_plain_kernel<NN_K><<<grid, 128, 0, st>>>(S, R, m, n, index_base, per, keys);
+    nn_plain_kernel<NN_K><<<grid, 128, 0, st>>>(S, R, m, n, index_base, per, keys, peer_keys);
     return cudaGetLastError();
 }
 

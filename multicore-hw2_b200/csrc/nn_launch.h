@@ -19,6 +19,7 @@ struct QregArgs
     uint32_t refs_per_split;  // references per split (multiple of 4; the last split takes what is left)
     unsigned long long *keys;
     float neg_zero;           // must be -0.0f: run-time addend of the exact fma(d, d, -0) square
+    int peer_keys;            // keys live in another GPU's memory: fold with system-scope atomics
 };
 
 struct RregArgs
@@ -30,6 +31,7 @@ struct RregArgs
     uint32_t index_base;
     unsigned long long *keys; // already offset to q0
     float neg_zero;           // must be -0.0f (see QregArgs)
+    int peer_keys;            // see QregArgs
 };
 
 // ---- per-K launchers (defined in nn_kernels_k.cu) -----------------------------------------
@@ -54,7 +56,7 @@ template <int K>
 cudaError_t query_rtma(int mq, LaunchInfo *info, int *tile_refs);
 template <int K>
 cudaError_t launch_plain(const float *S, const float *R, int m, uint32_t n, uint32_t index_base, uint32_t splits,
-                         unsigned long long *keys, cudaStream_t st);
+                         unsigned long long *keys, int peer_keys, cudaStream_t st);
 
 
 // AoS [n][k] -> SoA [k][n] repack (replaces mat_inv_kernel, core.cu:792-807).

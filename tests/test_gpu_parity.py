@@ -237,8 +237,9 @@ def test_config4_scaled_and_sharded(nn, oracle):
 
 
 def test_multi_gpu_host_entry(nn, oracle):
-    """v8's job: the host entry shards the references over all visible GPUs and merges the keys
-    with ncclAllReduce(min, uint64).  Needs >= 2 GPUs (gpurun --gpus 2); duplicates straddle the
+    """v8's job: the host entry shards the references over all visible GPUs and merges the keys --
+    by system-scope atomicMin into GPU 0's key array from inside every GPU's search kernel (default)
+    or with ncclAllReduce(min, uint64).  Needs >= 2 GPUs (gpurun --gpus 2); duplicates straddle the
     shard boundaries so the lowest-index rule is exercised across devices."""
     import torch
     g = torch.cuda.device_count()
@@ -249,7 +250,10 @@ def test_multi_gpu_host_entry(nn, oracle):
         S, R = cases.make(kind, 7000 + k, k, m, n)
         want = oracle.v0(S, R, threads=0)
         for gpus in sorted({2, g}):
-            assert np.array_equal(nn.search_host(S, R, num_gpus=gpus), want), (kind, gpus)
+            for p2p in (1, 0):  # fold into GPU 0's keys over NVLink inside the kernels / NCCL all-reduce
+                nn.set_option("p2p_merge", p2p)
+                assert np.array_equal(nn.search_host(S, R, num_gpus=gpus), want), (kind, gpus, p2p)
+    nn.set_option("p2p_merge", 1)
     # same through the reference's own entry point, all GPUs
     S, R = oracle.ta_sample(7)
     assert nn.cudaCallback(16, 1024, 65536, S, R).tolist() == TA["indices"][7]
