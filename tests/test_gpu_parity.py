@@ -123,6 +123,22 @@ def test_repack_soa_matches_mat_inv(nn, oracle, k, n):
     assert np.array_equal(got.view(np.uint32), oracle.repack_soa(R).view(np.uint32))
 
 
+@pytest.mark.parametrize("threads", [0, 1, 3])
+def test_pageable_inputs_through_the_staging_threads(nn, oracle, threads):
+    """The reference's harness passes malloc()ed arrays (generator.h:37, 44).  For pageable inputs the
+    host entry stages the reference chunks through pinned buffers on several host threads; small
+    chunks force many of them, with duplicated references straddling the chunk boundaries."""
+    S, R = cases.make("duplicated", 8800 + threads, 5, 77, 60013)
+    nn.set_option("h2d_chunk_bytes", 1)       # clamps to the minimum chunk of 4096 references
+    nn.set_option("stage_threads", threads)
+    try:
+        for _ in range(2):                    # second call reuses the staging buffers
+            assert np.array_equal(nn.search_host(S, R, num_gpus=1), oracle.v0(S, R, threads=0))
+    finally:
+        nn.set_option("h2d_chunk_bytes", 16 << 20)
+        nn.set_option("stage_threads", -1)
+
+
 def test_edge_shapes(nn, oracle):
     import torch
     from multicore_hw2_b200 import device
