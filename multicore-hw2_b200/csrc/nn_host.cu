@@ -947,7 +947,21 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
         chunk_bytes = std::min<int64_t>(chunk_bytes, 4 << 20);
     int64_t chunk_refs = std::max<int64_t>(4096, chunk_bytes / (int64_t)(k * sizeof(float)));
     chunk_refs = chunk_refs / 4096 * 4096; // keeps every chunk start 16-byte aligned and tile aligned
-    const size_t nchunks = count > 0 ? (size_t)((count + chunk_refs - 1) / chunk_refs) : 0;
+    // Chunk list.  Direct (pinned) path: the first chunks ramp up geometrically from 1/8 of the chunk
+    // size, so the search starts after a short first copy instead of a whole chunk's; staged path:
+    // uniform chunks (they are small already).
+    std::vector<std::pair<int64_t, int64_t>> chunks; // (first reference, count) relative to the shard
+    {
+        int64_t step = staged ? chunk_refs : std::max<int64_t>(4096, chunk_refs / 8 / 4096 * 4096);
+        for (int64_t off = 0; off < count;)
+        {
+            const int64_t cnt = std::min<int64_t>(step, count - off);
+            chunks.emplace_back(off, cnt);
+            off += cnt;
+            step = std::min<int64_t>(chunk_refs, step * 2);
+        }
+    }
+    const size_t nchunks = chunks.size();
     int rc = ensure_dev(c, dev, std::max<size_t>(bytesS, 16), std::max<size_t>(bytesR, 16), (size_t)std::max(m, 1),
                         nchunks + 1);
     if (rc)
@@ -997,8 +1011,7 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
                 for (size_t ci = t; ci < nchunks; ci += feeders, ++use)
                 {
                     const int b = (int)(use & 1);
-                    const int64_t off = (int64_t)ci * chunk_refs;
-                    const int64_t cnt = std::min<int64_t>(chunk_refs, count - off);
+                    const int64_t off = chunks[ci].first, cnt = chunks[ci].second;
                     const size_t bytes = (size_t)cnt * k * sizeof(float);
                     if (use >= 2 && (e = cudaEventSynchronize(c.stage_ev[t][b])) != cudaSuccess)
                         return bail(e, ci);
@@ -1029,8 +1042,7 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
 
     for (size_t ci = 0; ci < nchunks; ++ci)
     {
-        const int64_t off = (int64_t)ci * chunk_refs;
-        const int64_t cnt = std::min<int64_t>(chunk_refs, count - off);
+        const int64_t off = chunks[ci].first, cnt = chunks[ci].second;
         if (feeders > 0)
         {
             std::unique_lock<std::mutex> lk(fmu);
