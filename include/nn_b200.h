@@ -99,6 +99,24 @@ NN_B200_API int nn_b200_nearest_keys_soa(int k, int m, int64_t n, const float *d
                              uint32_t index_base, uint64_t *d_keys, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * 2b. Resident reference index: build once, query many times.
+ *     The reference pays the host->device copy of the reference set on every call
+ *     (core.cu:885-891); its only build-once/query-many variants are the KD-trees v9/v10
+ *     (build core.cu:984-1009, ask 1010-1026, use 1037-1047; README.md:335-344 reports query and total time
+ *     separately).  The same usage on the brute-force path: the shards stay in HBM (native AoS,
+ *     one contiguous shard per GPU, core.cu:875-883), a search moves only the queries and the
+ *     indices across PCIe.  Results are identical to nn_b200_search_host on the same data.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct nn_b200_index nn_b200_index;
+
+/* Uploads the n references (host, AoS [n][k]) to num_gpus devices (<= 0: all visible). */
+NN_B200_API int nn_b200_index_create(int k, int n, const float *referencePoints, int num_gpus, nn_b200_index **index);
+/* results[i] = index of the nearest resident reference of query i (m queries, host, AoS [m][k]). */
+NN_B200_API int nn_b200_index_search(nn_b200_index *index, int m, const float *searchPoints, int *results);
+NN_B200_API int nn_b200_index_info(const nn_b200_index *index, int *k, int64_t *n, int *gpus);
+NN_B200_API void nn_b200_index_destroy(nn_b200_index *index);
+
+/* ------------------------------------------------------------------------------------------
  * 3. Host-side helpers
  * ------------------------------------------------------------------------------------------ */
 

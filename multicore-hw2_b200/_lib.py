@@ -37,6 +37,10 @@ SIGNATURES = {
     "nn_b200_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "nn_b200_probe_fp32": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "nn_b200_plan_splits": (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.c_int64] * 2 + [ctypes.POINTER(ctypes.c_int64)] * 2),
+    "nn_b200_index_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "nn_b200_index_search": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "nn_b200_index_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int)]),
+    "nn_b200_index_destroy": (None, [ctypes.c_void_p]),
     "nn_b200_describe_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_char_p, ctypes.c_size_t]),
 }
 CXX_SYMBOL = "_Z12cudaCallbackiiiPfS_PPi"  # ::cudaCallback(int,int,int,float*,float*,int**), core.h:71

@@ -98,3 +98,49 @@ def probe_fp32(mode: int = 0, iters: int = 20000) -> float:
     v = ctypes.c_double()
     check(lib().nn_b200_probe_fp32(int(mode), iters, ctypes.byref(v)))
     return v.value
+
+
+class Index:
+    """Resident reference index (build once, query many): the reference set stays sharded in HBM and
+    a search moves only the queries and the indices over PCIe (include/nn_b200.h, section 2b).
+    Same results as :func:`search_host` on the same data."""
+
+    def __init__(self, referencePoints, k: int | None = None, num_gpus: int = 0):
+        R, r_ptr = _as_host(referencePoints)
+        if k is None:
+            k = int(R.shape[-1])
+        n = R.size // k if hasattr(R, "size") and not callable(R.size) else R.numel() // k
+        self._h = ctypes.c_void_p()
+        check(lib().nn_b200_index_create(k, n, r_ptr, num_gpus, ctypes.byref(self._h)))
+        self.k, self.n = k, n
+        g = ctypes.c_int()
+        check(lib().nn_b200_index_info(self._h, None, None, ctypes.byref(g)))
+        self.gpus = g.value
+
+    def search(self, searchPoints, out=None) -> np.ndarray:
+        if not self._h:
+            raise ValueError("index is closed")
+        S, s_ptr = _as_host(searchPoints)
+        m = S.size // self.k if hasattr(S, "size") and not callable(S.size) else S.numel() // self.k
+        if out is None:
+            out = np.empty(m, dtype=np.int32)
+        o, o_ptr = _as_host(out, dtype="int32")
+        check(lib().nn_b200_index_search(self._h, m, s_ptr, o_ptr))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            lib().nn_b200_index_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

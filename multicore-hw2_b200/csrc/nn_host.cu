@@ -1114,22 +1114,13 @@ int ensure_comms(int gpus)
 }
 } // namespace
 
-extern "C" int nn_b200_search_host(int k, int m, int n, const float *S, const float *R, int *results, int num_gpus)
+// Common driver of a sharded search on `gpus` devices: sets up the merge, runs enqueue(g, keys0,
+// keys_ready) for every device (one host thread each when there are several), merges, unpacks on
+// device 0 and copies the m indices to `results`.  Caller holds g_ctx.mu.
+template <class Enqueue>
+static int run_sharded(int m, int gpus, Enqueue enqueue, int *results)
 {
-    int rc = check_shape(k, m, n);
-    if (rc)
-        return rc;
-    if (m == 0)
-        return NN_B200_OK;
-    if (!S || !results || (n > 0 && !R))
-        return fail(NN_B200_EINVAL, "null host pointer");
-    int gpus = nn_b200_device_count(n > 0 ? n : 1);
-    if (gpus < 1)
-        return fail(NN_B200_ENODEV, "no CUDA device visible (this build has no CPU fallback)");
-    if (num_gpus > 0)
-        gpus = std::min(gpus, num_gpus);
-
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    int rc = NN_B200_OK;
     g_active_gpus = gpus;
     int prev_dev = 0;
     CU(cudaGetDevice(&prev_dev));
@@ -1161,9 +1152,7 @@ extern "C" int nn_b200_search_host(int k, int m, int n, const float *S, const fl
     std::vector<int> rcs(gpus, 0);
     std::vector<std::string> errs(gpus);
     auto work = [&](int g) {
-        int64_t b = 0, cnt = 0;
-        nn_b200_shard_range(n, gpus, g, &b, &cnt);
-        rcs[g] = enqueue_device(g_ctx.devs[g], g, k, m, S, R, b, cnt, keys0, keys_ready);
+        rcs[g] = enqueue(g, keys0, keys_ready);
         if (rcs[g])
             errs[g] = t_err;
     };
@@ -1235,6 +1224,185 @@ extern "C" int nn_b200_search_host(int k, int m, int n, const float *S, const fl
     memcpy(results, c0.hOut, (size_t)m * sizeof(int));
     CU(cudaSetDevice(prev_dev));
     return NN_B200_OK;
+}
+
+extern "C" int nn_b200_search_host(int k, int m, int n, const float *S, const float *R, int *results, int num_gpus)
+{
+    int rc = check_shape(k, m, n);
+    if (rc)
+        return rc;
+    if (m == 0)
+        return NN_B200_OK;
+    if (!S || !results || (n > 0 && !R))
+        return fail(NN_B200_EINVAL, "null host pointer");
+    int gpus = nn_b200_device_count(n > 0 ? n : 1);
+    if (gpus < 1)
+        return fail(NN_B200_ENODEV, "no CUDA device visible (this build has no CPU fallback)");
+    if (num_gpus > 0)
+        gpus = std::min(gpus, num_gpus);
+
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    return run_sharded(m, gpus,
+                       [&](int g, unsigned long long *keys0, cudaEvent_t keys_ready) {
+                           int64_t b = 0, cnt = 0;
+                           nn_b200_shard_range(n, gpus, g, &b, &cnt);
+                           return enqueue_device(g_ctx.devs[g], g, k, m, S, R, b, cnt, keys0, keys_ready);
+                       },
+                       results);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resident reference index: build once, query many times
+// ---------------------------------------------------------------------------------------------
+struct nn_b200_index
+{
+    int k = 0;
+    int64_t n = 0;
+    int gpus = 0;
+    std::vector<float *> dR;          // per device: its contiguous shard, native AoS
+    std::vector<int64_t> begin, count; // shard ranges
+};
+
+extern "C" void nn_b200_index_destroy(nn_b200_index *ix)
+{
+    if (!ix)
+        return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int g = 0; g < (int)ix->dR.size(); ++g)
+        if (ix->dR[g])
+        {
+            cudaSetDevice(g);
+            cudaFree(ix->dR[g]);
+        }
+    cudaSetDevice(prev);
+    (void)cudaGetLastError();
+    delete ix;
+}
+
+extern "C" int nn_b200_index_create(int k, int n, const float *R, int num_gpus, nn_b200_index **out)
+{
+    int rc = check_shape(k, 0, n);
+    if (rc)
+        return rc;
+    if (!out || (n > 0 && !R))
+        return fail(NN_B200_EINVAL, "null pointer");
+    *out = nullptr;
+    int gpus = nn_b200_device_count(n > 0 ? n : 1);
+    if (gpus < 1)
+        return fail(NN_B200_ENODEV, "no CUDA device visible (this build has no CPU fallback)");
+    if (num_gpus > 0)
+        gpus = std::min(gpus, num_gpus);
+    int prev_dev = 0;
+    CU(cudaGetDevice(&prev_dev));
+    nn_b200_index *ix = new nn_b200_index;
+    ix->k = k;
+    ix->n = n;
+    ix->gpus = gpus;
+    ix->dR.assign(gpus, nullptr);
+    ix->begin.assign(gpus, 0);
+    ix->count.assign(gpus, 0);
+    std::vector<int> rcs(gpus, 0);
+    std::vector<std::string> errs(gpus);
+    auto load = [&](int g) {
+        auto body = [&]() -> int {
+            nn_b200_shard_range(n, gpus, g, &ix->begin[g], &ix->count[g]);
+            DevInfo di;
+            int r = dev_info(g, &di); // refuses anything but sm_100
+            if (r)
+                return r;
+            CU(cudaSetDevice(g));
+            const size_t bytes = (size_t)ix->count[g] * k * sizeof(float);
+            CU(cudaMalloc(&ix->dR[g], std::max<size_t>(bytes, 16)));
+            if (bytes)
+                CU(cudaMemcpy(ix->dR[g], R + (size_t)ix->begin[g] * k, bytes, cudaMemcpyHostToDevice));
+            return NN_B200_OK;
+        };
+        rcs[g] = body();
+        if (rcs[g])
+            errs[g] = t_err;
+    };
+    if (gpus == 1)
+        load(0);
+    else
+    {
+        std::vector<std::thread> th;
+        for (int g = 0; g < gpus; ++g)
+            th.emplace_back(load, g);
+        for (auto &t : th)
+            t.join();
+    }
+    cudaSetDevice(prev_dev);
+    for (int g = 0; g < gpus; ++g)
+        if (rcs[g])
+        {
+            t_err = errs[g];
+            const int r = rcs[g];
+            nn_b200_index_destroy(ix);
+            return r;
+        }
+    *out = ix;
+    return NN_B200_OK;
+}
+
+extern "C" int nn_b200_index_info(const nn_b200_index *ix, int *k, int64_t *n, int *gpus)
+{
+    if (!ix)
+        return fail(NN_B200_EINVAL, "null index");
+    if (k)
+        *k = ix->k;
+    if (n)
+        *n = ix->n;
+    if (gpus)
+        *gpus = ix->gpus;
+    return NN_B200_OK;
+}
+
+extern "C" int nn_b200_index_search(nn_b200_index *ix, int m, const float *S, int *results)
+{
+    if (!ix)
+        return fail(NN_B200_EINVAL, "null index");
+    int rc = check_shape(ix->k, m, ix->n);
+    if (rc)
+        return rc;
+    if (m == 0)
+        return NN_B200_OK;
+    if (!S || !results)
+        return fail(NN_B200_EINVAL, "null host pointer");
+    const int k = ix->k;
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    return run_sharded(m, ix->gpus,
+                       [&](int g, unsigned long long *keys0, cudaEvent_t keys_ready) -> int {
+                           DevCtx &c = g_ctx.devs[g];
+                           const size_t bytesS = (size_t)m * k * sizeof(float);
+                           int r = ensure_dev(c, g, std::max<size_t>(bytesS, 16), 16, (size_t)m, 1);
+                           if (r)
+                               return r;
+                           CU(cudaMemcpyAsync(c.dS, S, bytesS, cudaMemcpyHostToDevice, c.copy));
+                           CU(cudaEventRecord(c.events[0], c.copy));
+                           unsigned long long *keys = keys0 ? keys0 : c.dKeys;
+                           if (keys0)
+                               CU(cudaStreamWaitEvent(c.compute, keys_ready, 0));
+                           else
+                           {
+                               r = nn_b200_keys_init(reinterpret_cast<uint64_t *>(c.dKeys), m, c.compute);
+                               if (r)
+                                   return r;
+                           }
+                           CU(cudaStreamWaitEvent(c.compute, c.events[0], 0));
+                           if (ix->count[g] > 0)
+                           {
+                               r = nearest_keys_impl(k, m, ix->count[g], c.dS, ix->dR[g], (uint32_t)ix->begin[g],
+                                                     reinterpret_cast<uint64_t *>(keys), c.compute, false, keys0 ? 1 : 0);
+                               if (r)
+                                   return r;
+                           }
+                           if (!c.done)
+                               CU(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+                           CU(cudaEventRecord(c.done, c.compute));
+                           return NN_B200_OK;
+                       },
+                       results);
 }
 
 extern "C" void nn_b200_cudaCallback(int k, int m, int n, float *searchPoints, float *referencePoints, int **results)

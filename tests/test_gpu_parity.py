@@ -139,6 +139,25 @@ def test_pageable_inputs_through_the_staging_threads(nn, oracle, threads):
         nn.set_option("stage_threads", -1)
 
 
+def test_resident_index_build_once_query_many(nn, oracle):
+    """nn_b200_index_*: the references stay in HBM, several query batches of different sizes (each
+    kernel family: 1, 7, 300 queries) are answered against them; identical to v0 and to the
+    one-shot host entry.  Also on every GPU count available."""
+    import torch
+    S, R = cases.make("duplicated", 4711, 6, 300, 70001)
+    want = oracle.v0(S, R, threads=0)
+    for gpus in sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()}):
+        with nn.Index(R, num_gpus=gpus) as ix:
+            assert (ix.k, ix.n, ix.gpus) == (6, 70001, gpus)
+            for lo, hi in [(0, 1), (1, 8), (0, 300), (293, 300)]:
+                assert np.array_equal(ix.search(S[lo:hi]), want[lo:hi]), (gpus, lo, hi)
+            assert ix.search(S[:0]).size == 0
+    with nn.Index(np.zeros((0, 3), np.float32), k=3) as ix:   # empty index: v0's start state, index 0
+        assert ix.search(np.ones((4, 3), np.float32)).tolist() == [0] * 4
+    with pytest.raises(nn.NNError):
+        nn.Index(np.zeros((5, 2), np.float32))
+
+
 def test_edge_shapes(nn, oracle):
     import torch
     from multicore_hw2_b200 import device
