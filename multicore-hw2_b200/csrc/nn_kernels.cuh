@@ -53,6 +53,9 @@
 #ifndef NN_RREG_L2PF
 #define NN_RREG_L2PF 0 // slot-batches ahead that a CTA asks the L2 to prefetch (0 = off; no gain measured)
 #endif
+#ifndef NN_RTMA_QUERY_REGS
+#define NN_RTMA_QUERY_REGS 0 // reference-stream kernel: keep the query pairs in registers (A/B)
+#endif
 #ifndef NN_RTMA_PIPELINE
 #define NN_RTMA_PIPELINE 1 // reference-stream kernel: software-pipeline the shared loads over half tiles
 #endif
@@ -964,13 +967,29 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
                 }
             }
         };
+        // query pairs kept in registers for the whole kernel where they fit (NP*K float2 = 2*NP*K
+        // registers): saves 4 shared loads per pair and half tile
+        constexpr bool QR = NN_RTMA_QUERY_REGS && (2 * NP * K <= 64);
+        float2 qall[QR ? NP * K : 1];
+        if constexpr (QR)
+        {
+#pragma unroll
+            for (int i = 0; i < NP * K; ++i)
+                qall[i] = sq[i];
+        }
         // minima of HP references against the MQ queries, folded into rm[] (FIRST: rm is unset)
         auto fold_half = [&](const float(&ref)[HP * K], float2(&rm)[NP], const bool FIRST) {
 #pragma unroll
             for (int pr = 0; pr < NP; ++pr)
             {
                 float2 qp[K];
-                if constexpr (K % 2 == 0)
+                if constexpr (QR)
+                {
+#pragma unroll
+                    for (int d = 0; d < K; ++d)
+                        qp[d] = qall[pr * K + d];
+                }
+                else if constexpr (K % 2 == 0)
                 {
                     const float4 *q4 = reinterpret_cast<const float4 *>(sq + pr * K);
 #pragma unroll
