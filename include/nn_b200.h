@@ -128,6 +128,12 @@ NN_B200_API int nn_b200_shard_range(int64_t n, int num_shards, int shard, int64_
 /* Number of CUDA devices the host entry would use for n references (core.cu:865-868). */
 NN_B200_API int nn_b200_device_count(int64_t n);
 
+/* Loads every search kernel (all k, all tile shapes) on the current device so that no later call
+ * pays the lazy code loading of a first use (about 1-3 ms per kernel).  The reference hides the same
+ * cold start with its static WarmUP object (core.cu:1274).  The host entry points call it once per
+ * device on first use unless the environment has NN_B200_WARMUP=0. */
+NN_B200_API int nn_b200_warmup(void);
+
 /* Kernels launched by this library in this process so far (bench.py's `gpu_launches`). */
 NN_B200_API int64_t nn_b200_launch_count(void);
 

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -255,6 +256,20 @@ int main(int argc, char **argv)
     printf("{\"device\":\"%s\",\"sms\":%d,\"max_clock_ghz\":%.3f,\"fp32_peak_ops\":%.4e}\n", prop.name, g_sms,
            g_clock_ghz, g_peak_ops);
 
+    if (sweep == "warmup")
+    {
+        CK(cudaFree(0));
+        for (int i = 0; i < 2; ++i)
+        {
+            cudaEvent_t a;
+            CK(cudaEventCreate(&a));
+            const auto t0 = std::chrono::steady_clock::now();
+            NN(nn_b200_warmup());
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            printf("{\"op\":\"warmup\",\"call\":%d,\"ms\":%.3f}\n", i, ms);
+        }
+        return 0;
+    }
     if (sweep == "probe")
     {
         const char *names[6] = {"scalar", "packed", "packed/scalar alternating", "4 packed + 4 scalar blocks",

@@ -59,6 +59,9 @@
 #ifndef NN_RTMA_PIPELINE
 #define NN_RTMA_PIPELINE 1 // reference-stream kernel: software-pipeline the shared loads over half tiles
 #endif
+#ifndef NN_QREG_UNROLL_NARROW
+#define NN_QREG_UNROLL_NARROW 1 // unroll the chunk loop 2x (Q = 4) / 4x (Q <= 2): -10% at Q = 1 and at k = 16, m = 1024; +-1% elsewhere
+#endif
 #ifndef NN_QREG_PREFETCH
 #define NN_QREG_PREFETCH 1 // query-register kernel: load the next reference group while computing the current one
 #endif
@@ -374,6 +377,10 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
     using C = QregCfg<K>;
     constexpr int CH = C::CH, TR = C::TR, STAGES = C::STAGES;
     constexpr bool PF = QregPrefetch<K, Q, MATH>::value;
+    // chunks unrolled in the tile loop: the narrow tiles have short chunks (Q/2 * (3K-1) * CH packed
+    // instructions), so the loop branch and the compare/select chain at the end of every chunk weigh
+    // more; unrolling lets the next chunk's arithmetic cover them
+    constexpr int UNR = NN_QREG_UNROLL_NARROW ? (Q >= 8 ? kQregUnroll : (Q >= 4 ? 2 : 4)) : kQregUnroll;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tiles = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
             for (int i = 0; i < Geo<K>::F4; ++i)
                 nxt[i] = reinterpret_cast<const float4 *>(sm)[i];
         }
-#pragma unroll kQregUnroll
+#pragma unroll UNR
         for (int c = 0; c < cnt; c += CH)
         {
             float cm[Q];
