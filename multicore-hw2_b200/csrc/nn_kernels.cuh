@@ -256,6 +256,15 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes
 // query at the end by re-scanning the winning chunk -- no per-pair index bookkeeping.
 // Work item = (query tile, reference split); results are folded with atomicMin on packed keys.
 // =============================================================================================
+// Queries per thread of the WIDE query-register tile: as many as fit beside one reference group in
+// a 128-register budget.  Narrower tiles (fewer queries per thread) serve small query counts.
+template <int K>
+struct QregDefault
+{
+    static constexpr int BUDGET = (96 - Geo<K>::G * K) / K;
+    static constexpr int Q = BUDGET >= 8 ? 8 : (BUDGET >= 4 ? 4 : (BUDGET >= 2 ? 2 : 1));
+};
+
 template <int K>
 struct QregCfg
 {
@@ -380,7 +389,7 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
     // chunks unrolled in the tile loop: the narrow tiles have short chunks (Q/2 * (3K-1) * CH packed
     // instructions), so the loop branch and the compare/select chain at the end of every chunk weigh
     // more; unrolling lets the next chunk's arithmetic cover them
-    constexpr int UNR = NN_QREG_UNROLL_NARROW ? (Q >= 8 ? kQregUnroll : (Q >= 4 ? 2 : 4)) : kQregUnroll;
+    constexpr int UNR = (NN_QREG_UNROLL_NARROW && Q < QregDefault<K>::Q) ? (Q >= 4 ? 2 : 4) : kQregUnroll;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tiles = reinterpret_cast<float *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);

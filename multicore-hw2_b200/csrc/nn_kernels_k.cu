@@ -12,15 +12,6 @@
 namespace nnb200
 {
 
-// Queries per thread of the wide query-register tile: as many as fit beside one reference group
-// in a 128-register budget.
-template <int K>
-struct QregDefault
-{
-    static constexpr int BUDGET = (96 - Geo<K>::G * K) / K;
-    static constexpr int Q = BUDGET >= 8 ? 8 : (BUDGET >= 4 ? 4 : (BUDGET >= 2 ? 2 : 1));
-};
-
 template <int K, int Q, int NT, int MATH>
 static cudaError_t launch_qreg_one(const QregArgs &a, uint32_t qtiles, cudaStream_t st)
 {
