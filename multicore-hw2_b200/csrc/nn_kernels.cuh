@@ -795,6 +795,10 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
 // large fully-used bursts, and no warp ever waits on a global load inside the math.
 // (ncu on kernel B at k = 8, m = 8: 27% more DRAM sectors than the reference set holds, FMA pipe
 // 63% active with long-scoreboard the top stall -- profiles/r01_ncu_summary.txt.)
+// Measured alternatives that did not win at k = 8, m = 8, n = 2^26 (0.409 ms here): two CTAs of 8+1
+// warps per SM (0.43-0.44 ms), 16+1 warps (0.42), query pairs held in registers (0.44, spills at
+// 12 warps), and per-warp private rings without a producer warp (each warp fetching its own 4 KB
+// slice: 0.407 ms at 16 warps, but 3-4% slower at k = 3 and k = 16).
 // Tile t of the reference set goes to CTA t % gridDim.x (persistent grid); the ragged end of the set
 // (n % TILE_REFS references) is read with plain loads by the CTA whose turn it is.
 // =============================================================================================
