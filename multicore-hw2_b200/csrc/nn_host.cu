@@ -296,14 +296,25 @@ static double qreg_model_cycles(int k, int q, int occ, int sms, int64_t m, int64
     const double f_q = q >= 8 ? 1.0 : (q >= 4 ? 0.988 : (q >= 2 ? 0.965 : 1.0 / 1.3));
     const double cpr = (q >= 2 ? (q / 2) * (3.0 * k - 1.0) * 2.0 : (3.0 * k - 1.0)) / f_q;
     auto eff = [](int64_t c) { return c <= 1 ? 0.58 : (c == 2 ? 0.78 : (c == 3 ? 0.86 : 0.92)); };
-    const double ovh = 5000.0 + 600.0 * q;
+    // Per-CTA prologue (query loads) and epilogue (re-read of the Q winning 4-point chunks): every
+    // load instruction of a warp touches 32 different sectors, so it costs ~32 LSU cycles; the CTAs
+    // of an SM share the LSU.  Narrow tiles use vector loads there, the widest tile scalar ones
+    // (nn_kernels.cuh, VEC); about half of it hides behind other CTAs' arithmetic.
+    const int g = (k % 4 == 0) ? 1 : ((k % 2 == 0) ? 2 : 4);
+    const int budget = (96 - g * k) / k;
+    const int qwide = budget >= 8 ? 8 : (budget >= 4 ? 4 : (budget >= 2 ? 2 : 1));
+    const bool vec = q < qwide;
+    const double loads = vec ? (double)q * k / (k % 4 == 0 ? 4 : (k % 2 == 0 ? 2 : 1)) + (double)q * k
+                             : (double)q * k + 4.0 * q * k;
+    const double lsu = loads * 32.0 * 4.0 * 0.5;
+    const double ovh = 5000.0;
     const int64_t slots = (int64_t)sms * occ;
     const int64_t full_waves = total / slots, rem = total % slots;
-    double t = (double)full_waves * (ovh + (double)occ * (double)rps * cpr / eff(occ));
+    double t = (double)full_waves * (ovh + (double)occ * (lsu + (double)rps * cpr / eff(occ)));
     if (rem)
     {
         const int64_t c = (rem + sms - 1) / sms;
-        t += ovh + (double)c * (double)rps * cpr / eff(c);
+        t += ovh + (double)c * (lsu + (double)rps * cpr / eff(c));
     }
     return t;
 }

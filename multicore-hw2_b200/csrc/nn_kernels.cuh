@@ -386,6 +386,12 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
     using C = QregCfg<K>;
     constexpr int CH = C::CH, TR = C::TR, STAGES = C::STAGES;
     constexpr bool PF = QregPrefetch<K, Q, MATH>::value;
+    // Narrow tiles run with little work per CTA, where the query loads of the prologue and the
+    // re-read of the winning chunks in the epilogue weigh (ncu at k=16, m=1024, n=65536: lg/mio
+    // throttle and long-scoreboard stalls from 64..256 scalar loads per thread, each touching 32
+    // sectors per warp): they use 128-bit loads there.  The widest tile keeps the scalar forms, whose
+    // register footprint lets it run 4 CTAs per SM.
+    constexpr bool VEC = Q < QregDefault<K>::Q;
     // chunks unrolled in the tile loop: the narrow tiles have short chunks (Q/2 * (3K-1) * CH packed
     // instructions), so the loop branch and the compare/select chain at the end of every chunk weigh
     // more; unrolling lets the next chunk's arithmetic cover them
@@ -428,6 +434,8 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
     }
 
     // this thread's queries (clamped so that out-of-range slots compute on a valid row)
+    const bool s_align16 = (reinterpret_cast<uintptr_t>(a.S) & 15) == 0;
+    const bool s_align8 = (reinterpret_cast<uintptr_t>(a.S) & 7) == 0;
     float q[Q][K];
     float best[Q];
     uint32_t bref[Q];
@@ -438,9 +446,36 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
         int qi = (int)(qtile * (NT * Q)) + j * NT + tid;
         qi = qi < a.m ? qi : a.m - 1;
         const float *src = a.S + (size_t)qi * K;
+        // rows of 4n (2n) floats are 16 (8) byte aligned when the query array is: vector loads cut the
+        // load instructions -- each touches 32 different sectors per warp -- by 4 (2)
+        if (VEC && K % 4 == 0 && s_align16)
+        {
 #pragma unroll
-        for (int i = 0; i < K; ++i)
-            q[j][i] = __ldg(src + i);
+            for (int i = 0; i < K / 4; ++i)
+            {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
+                q[j][4 * i + 0] = v.x;
+                q[j][4 * i + 1] = v.y;
+                q[j][4 * i + 2] = v.z;
+                q[j][4 * i + 3] = v.w;
+            }
+        }
+        else if (VEC && K % 2 == 0 && s_align8)
+        {
+#pragma unroll
+            for (int i = 0; i < K / 2; ++i)
+            {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(src) + i);
+                q[j][2 * i + 0] = v.x;
+                q[j][2 * i + 1] = v.y;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+                q[j][i] = __ldg(src + i);
+        }
         best[j] = __int_as_float(0x7f800000);
         bref[j] = NO_REF;
     }
@@ -513,15 +548,47 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
         if (bref[j] != NO_REF && qi < a.m)
         {
             uint32_t idx = bref[j];
-#pragma unroll
-            for (int c = CH - 1; c >= 0; --c)
+            if (VEC && bref[j] + CH <= a.n)
             {
-                const uint32_t r = bref[j] + c;
-                if (r < a.n)
+                // whole chunk inside the set: it starts on a 16-byte boundary (chunk starts are
+                // multiples of 4 points), so it is re-read group by group with 128-bit loads -- a
+                // quarter of the load instructions, each of which touches 32 sectors per warp
+                constexpr int G = Geo<K>::G, F4 = Geo<K>::F4;
+                const float4 *p4 = reinterpret_cast<const float4 *>(a.R + (size_t)bref[j] * K);
+#pragma unroll
+                for (int g0 = CH - G; g0 >= 0; g0 -= G)
                 {
-                    const float d = sqdist_gmem<K>(q[j], a.R + (size_t)r * K);
-                    if (d == best[j])
-                        idx = r;
+                    float grp[G * K];
+#pragma unroll
+                    for (int i = 0; i < F4; ++i)
+                    {
+                        const float4 v = __ldg(p4 + (g0 / G) * F4 + i);
+                        grp[4 * i + 0] = v.x;
+                        grp[4 * i + 1] = v.y;
+                        grp[4 * i + 2] = v.z;
+                        grp[4 * i + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int g = G - 1; g >= 0; --g)
+                    {
+                        const float d = sqdist<K, 0, false>(q[j], &grp[g * K]);
+                        if (d == best[j])
+                            idx = bref[j] + g0 + g;
+                    }
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int c = CH - 1; c >= 0; --c)
+                {
+                    const uint32_t r = bref[j] + c;
+                    if (r < a.n)
+                    {
+                        const float d = sqdist_gmem<K>(q[j], a.R + (size_t)r * K);
+                        if (d == best[j])
+                            idx = r;
+                    }
                 }
             }
             fold_key(a.keys + qi, pack_key(best[j], a.index_base + idx), a.peer_keys);
