@@ -53,6 +53,12 @@
 #ifndef NN_RREG_L2PF
 #define NN_RREG_L2PF 0 // slot-batches ahead that a CTA asks the L2 to prefetch (0 = off; no gain measured)
 #endif
+#ifndef NN_RTMA_ROTATE
+#define NN_RTMA_ROTATE 1 // reference-stream kernel, k = 16: bank-conflict-free rotated chunk reads (m=8, n=2^25: 0.521 -> 0.444 ms)
+#endif
+#ifndef NN_RTMA_ROTATE2
+#define NN_RTMA_ROTATE2 0 // same idea for k = 8 (2-way conflict): measured 3% SLOWER at k=8, m=8 (0.422 vs 0.409 ms)
+#endif
 #ifndef NN_RTMA_QUERY_REGS
 #define NN_RTMA_QUERY_REGS 0 // reference-stream kernel: keep the query pairs in registers (A/B)
 #endif
@@ -890,6 +896,69 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
     return ok != 0;
 }
 
+// One thread's reference group (F4 float4) out of a shared-memory tile.  When consecutive lanes'
+// groups are 64 bytes apart modulo 128 (k = 16: one 64-byte point per lane) the four 16-byte chunks
+// of lanes l and l+2 fall into the same banks: a 4-way conflict on every LDS.128, which made the
+// shared-memory pipe as busy as the FMA pipe.  There each lane reads its chunks in an order rotated
+// by (lane/2)%4, which spreads a quarter-warp over all eight 16-byte bank groups, and rotates the
+// registers back with two select stages (ALU pipe, which has room).
+template <int K>
+__device__ __forceinline__ void lds_group(const float4 *__restrict__ p4, float *dst, const int lane)
+{
+    constexpr int F4 = Geo<K>::F4;
+    constexpr bool ROT = NN_RTMA_ROTATE && (F4 == 4) && ((F4 * 16) % 128 == 64);
+    if constexpr (ROT)
+    {
+        const int rot = (lane >> 1) & 3;
+        float4 v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            v[c] = p4[(c + rot) & 3]; // v[c] = chunk (c + rot) & 3
+        const bool r1 = rot & 1, r2 = rot & 2;
+        float4 t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        { // undo the odd part: t[j] = chunk (j + (rot & 2)) & 3
+            const float4 a = v[j], b = v[(j + 3) & 3];
+            t[j] = make_float4(r1 ? b.x : a.x, r1 ? b.y : a.y, r1 ? b.z : a.z, r1 ? b.w : a.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        { // undo the even part: chunk j
+            const float4 a = t[j], b = t[(j + 2) & 3];
+            dst[4 * j + 0] = r2 ? b.x : a.x;
+            dst[4 * j + 1] = r2 ? b.y : a.y;
+            dst[4 * j + 2] = r2 ? b.z : a.z;
+            dst[4 * j + 3] = r2 ? b.w : a.w;
+        }
+    }
+    else if constexpr (NN_RTMA_ROTATE2 && F4 == 2)
+    { // k = 8: 32-byte points, lanes l and l+4 collide (2-way): lanes 4..7 of every 8 swap the halves
+        const bool sw = (lane >> 2) & 1;
+        const float4 a = p4[sw ? 1 : 0], b = p4[sw ? 0 : 1];
+        dst[0] = sw ? b.x : a.x;
+        dst[1] = sw ? b.y : a.y;
+        dst[2] = sw ? b.z : a.z;
+        dst[3] = sw ? b.w : a.w;
+        dst[4] = sw ? a.x : b.x;
+        dst[5] = sw ? a.y : b.y;
+        dst[6] = sw ? a.z : b.z;
+        dst[7] = sw ? a.w : b.w;
+    }
+    else
+    {
+#pragma unroll
+        for (int f = 0; f < F4; ++f)
+        {
+            const float4 v = p4[f];
+            dst[4 * f + 0] = v.x;
+            dst[4 * f + 1] = v.y;
+            dst[4 * f + 2] = v.z;
+            dst[4 * f + 3] = v.w;
+        }
+    }
+}
+
 template <int K, int PT, int NW, int STAGES>
 struct RtmaCfg
 {
@@ -1042,16 +1111,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
 #pragma unroll
             for (int i = 0; i < HT; ++i)
             {
-                const float4 *p4 = t4 + (size_t)((half * HT + i) * NTC + tid) * F4;
-#pragma unroll
-                for (int f = 0; f < F4; ++f)
-                {
-                    const float4 v = p4[f];
-                    dst[i * G * K + 4 * f + 0] = v.x;
-                    dst[i * G * K + 4 * f + 1] = v.y;
-                    dst[i * G * K + 4 * f + 2] = v.z;
-                    dst[i * G * K + 4 * f + 3] = v.w;
-                }
+                lds_group<K>(t4 + (size_t)((half * HT + i) * NTC + tid) * F4, &dst[i * G * K], lane);
             }
         };
         // query pairs kept in registers for the whole kernel where they fit (NP*K float2 = 2*NP*K
@@ -1179,16 +1239,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
 #pragma unroll
             for (int i = 0; i < PT; ++i)
             {
-                const float4 *p4 = t4 + (size_t)(i * NTC + tid) * F4;
-#pragma unroll
-                for (int f = 0; f < F4; ++f)
-                {
-                    const float4 v = p4[f];
-                    ref[i * G * K + 4 * f + 0] = v.x;
-                    ref[i * G * K + 4 * f + 1] = v.y;
-                    ref[i * G * K + 4 * f + 2] = v.z;
-                    ref[i * G * K + 4 * f + 3] = v.w;
-                }
+                lds_group<K>(t4 + (size_t)(i * NTC + tid) * F4, &ref[i * G * K], lane);
             }
             __syncwarp();
             if (lane == 0)
