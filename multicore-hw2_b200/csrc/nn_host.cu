@@ -374,10 +374,10 @@ static int make_plan_uncached(int k, int m, int64_t n, bool soa, const DevInfo &
     // on the FP32 pipe matters as well and the TMA-ring kernel wins at every k (B200 sweeps in
     // profiles/); beyond ~112 queries the query-register kernel's 128-query tile is full enough.
     // Between them, 5..112 queries: the reference-stream kernel re-streams the set once per pass of 8
-    // queries and pays ~12 us of pipeline fill and drain per pass, the query-register kernel streams
-    // it once but computes on a 128-query tile however few queries there are.  Fitted to the B200
-    // sweep of profiles/README.md (k = 3, 8, 16; m = 8, 32, 100; n = 2^16 .. 2^22), in microseconds:
-    //   t_stream = 5 + passes * (12 + max(0.787, 0.755) * n*k / 1e6)     t_tile = 4 + 13.8 * n*k / 1e6
+    // queries and pays ~7.5 us of pipeline fill, merge and drain per pass, the query-register kernel
+    // streams it once but computes on a 128-query tile however few queries there are.  Fitted to the
+    // B200 sweeps of profiles/README.md (k = 3, 8, 16; m = 8, 32, 100; n = 2^16 .. 2^24), microseconds:
+    //   t_stream = 5 + passes * (7.5 + 0.787 * n*k / 1e6)     t_tile = 4 + 13.8 * n*k / 1e6
     if (variant == 0)
     {
         if (m <= 4)
@@ -385,7 +385,7 @@ static int make_plan_uncached(int k, int m, int64_t n, bool soa, const DevInfo &
         else if (m <= g_opt.rreg_max_m.load())
         {
             const double x = (double)n * k * 1e-6, passes = (double)((m + 7) / 8);
-            const double t_stream = 5.0 + passes * (12.0 + 0.787 * x), t_tile = 4.0 + 13.8 * x;
+            const double t_stream = 5.0 + passes * (7.5 + 0.787 * x), t_tile = 4.0 + 13.8 * x;
             variant = t_stream < t_tile ? 4 : 1;
         }
         else

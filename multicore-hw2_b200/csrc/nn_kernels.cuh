@@ -59,9 +59,6 @@
 #ifndef NN_RTMA_ROTATE2
 #define NN_RTMA_ROTATE2 0 // same idea for k = 8 (2-way conflict): measured 3% SLOWER at k=8, m=8 (0.422 vs 0.409 ms)
 #endif
-#ifndef NN_RTMA_EPILOGUE_PREFETCH
-#define NN_RTMA_EPILOGUE_PREFETCH 1 // reference-stream kernel: prefetch the lines of the index resolution
-#endif
 #ifndef NN_RTMA_QUERY_REGS
 #define NN_RTMA_QUERY_REGS 0 // reference-stream kernel: keep the query pairs in registers (A/B)
 #endif
@@ -1270,11 +1267,60 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
         fold_tile(ref, nfull);
     }
 
-    // Warp-level merge, as in kernel B: only lanes that hold the warp minimum resolve their exact
-    // (lowest) index by re-reading their references of the winning tile.  The re-reads of the MQ
-    // queries sit in divergent branches, one memory round trip after the other; so first every
-    // candidate (lane, query) asks for its lines with prefetches, which all go out back to back.
+    // Warp-level merge.  For every query the lanes whose minimum equals the warp minimum are the
+    // candidates (usually one; several on ties), and each candidate's exact answer is the lowest
+    // index among ITS references of its winning tile at that distance.  The references are re-read
+    // COOPERATIVELY -- the whole warp loads the candidate's P*K floats, one float per lane -- and the
+    // loads of all MQ queries are issued before the first one is used: one memory round trip per
+    // pass instead of one per query in divergent branches (that serial chain cost ~11 us per pass,
+    // more than the arithmetic of a pass over 2^20 references).  Lane p < P then rebuilds reference
+    // p from the lanes' registers with shuffles and evaluates it with v0's arithmetic.
+    constexpr int F = P * K;             // floats of one thread's references in a tile
+    constexpr int NV = (F + 31) / 32;    // registers per lane holding them
+    const int warp_tid0 = tid - lane;    // first consumer thread of this warp
+    auto load_cand = [&](uint32_t tile, int src, float(&v)[NV]) {
+#pragma unroll
+        for (int u = 0; u < NV; ++u)
+        {
+            const int e = lane + 32 * u; // float number e of the candidate's P*K
+            const int i = e / (G * K), off = e % (G * K);
+            const uint32_t r = tile * TILE_REFS + (uint32_t)(i * NTC + warp_tid0 + src) * G; // first point of the group
+            const bool ok = e < F && r + (uint32_t)(off / K) < a.n;
+            v[u] = ok ? __ldg(a.R + (size_t)r * K + off) : __int_as_float(0x7fffffff);
+        }
+    };
+    // lowest index among the candidate's references whose distance to query j is exactly wmin
+    auto eval_cand = [&](int j, uint32_t tile, int src, const float(&v)[NV], float wmin) -> uint32_t {
+        const int pme = lane < P ? lane : P - 1; // lane p evaluates reference p
+        float rr[K];
+#pragma unroll
+        for (int d = 0; d < K; ++d)
+        {
+            const int e = pme * K + d;
+            float x = __shfl_sync(0xffffffffu, v[0], e & 31);
+            if constexpr (NV > 1)
+            {
+                const float y = __shfl_sync(0xffffffffu, v[1], e & 31);
+                x = (e >> 5) ? y : x;
+            }
+            rr[d] = x;
+        }
+        float qv[K];
+#pragma unroll
+        for (int d = 0; d < K; ++d)
+            qv[d] = (j & 1) ? sq[(j / 2) * K + d].y : sq[(j / 2) * K + d].x;
+        const float d2 = sqdist<K, 0, false>(qv, rr);
+        const uint32_t r = tile * TILE_REFS + (uint32_t)((pme / G) * NTC + warp_tid0 + src) * G + (uint32_t)(pme % G);
+        uint32_t idx = (lane < P && r < a.n && d2 == wmin) ? r : NO_REF;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            idx = min(idx, __shfl_xor_sync(0xffffffffu, idx, o));
+        return idx;
+    };
+
     float wmins[MQ];
+    uint32_t masks[MQ], tiles[MQ];
+    float vals[MQ][NV];
 #pragma unroll
     for (int j = 0; j < MQ; ++j)
     {
@@ -1283,70 +1329,28 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
         for (int o = 16; o > 0; o >>= 1)
             wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
         wmins[j] = wmin;
-    }
-    if (NN_RTMA_EPILOGUE_PREFETCH && mine >= 64) // pays only behind a long stream (A/B: +1..3% there, -4% on short ones)
-    {
-#pragma unroll
-        for (int j = 0; j < MQ; ++j)
-            if (bref[j] != NO_REF && best[j] == wmins[j])
-            {
-#pragma unroll
-                for (int i = 0; i < PT; ++i)
-                {
-                    const uint32_t r = bref[j] * TILE_REFS + (uint32_t)(i * NTC + tid) * G;
-                    if (r < a.n)
-                    {
-                        const char *p = reinterpret_cast<const char *>(a.R + (size_t)r * K);
-                        const size_t last = (size_t)min((uint32_t)G, a.n - r) * K * 4 - 4;
-#pragma unroll
-                        for (int b = 0; b < G * K * 4; b += 128)
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + min((size_t)b, last)));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + last));
-                    }
-                }
-            }
+        masks[j] = __ballot_sync(0xffffffffu, bref[j] != NO_REF && best[j] == wmin);
+        const int src = masks[j] ? __ffs(masks[j]) - 1 : 0;
+        tiles[j] = __shfl_sync(0xffffffffu, bref[j], src);
+        if (masks[j]) // (warp-uniform)
+            load_cand(tiles[j], src, vals[j]);
     }
 #pragma unroll
     for (int j = 0; j < MQ; ++j)
     {
-        const float wmin = wmins[j];
-        unsigned long long key = KEY_INIT | NO_REF;
-        if (bref[j] != NO_REF && best[j] == wmin)
-        {
-            float qv[K];
-#pragma unroll
-            for (int d = 0; d < K; ++d)
-                qv[d] = (j & 1) ? sq[(j / 2) * K + d].y : sq[(j / 2) * K + d].x;
-            uint32_t idx = 0;
-#pragma unroll
-            for (int i = PT - 1; i >= 0; --i)
-            {
-#pragma unroll
-                for (int g = G - 1; g >= 0; --g)
-                {
-                    const uint32_t r = bref[j] * TILE_REFS + (uint32_t)(i * NTC + tid) * G + g;
-                    if (r < a.n)
-                    {
-                        float rr[K];
-#pragma unroll
-                        for (int d = 0; d < K; ++d)
-                            rr[d] = __ldg(a.R + (size_t)r * K + d);
-                        const float d2 = sqdist<K, 0, false>(qv, rr);
-                        if (d2 == best[j])
-                            idx = r;
-                    }
-                }
-            }
-            key = pack_key(best[j], a.index_base + idx);
+        if (!masks[j])
+            continue; // nothing beat the start state for this query in this warp
+        uint32_t idx = eval_cand(j, tiles[j], __ffs(masks[j]) - 1, vals[j], wmins[j]);
+        for (uint32_t rest = masks[j] & (masks[j] - 1); rest; rest &= rest - 1)
+        { // further lanes tied at the warp minimum (rare): same procedure, one after the other
+            const int src = __ffs(rest) - 1;
+            const uint32_t tile = __shfl_sync(0xffffffffu, bref[j], src);
+            float v[NV];
+            load_cand(tile, src, v);
+            idx = min(idx, eval_cand(j, tile, src, v, wmins[j]));
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-            key = other < key ? other : key;
-        }
-        if (lane == 0 && j < valid_q && key < (KEY_INIT | NO_REF))
-            fold_key(a.keys + q0 + j, key, a.peer_keys);
+        if (lane == 0 && j < valid_q)
+            fold_key(a.keys + q0 + j, pack_key(wmins[j], a.index_base + idx), a.peer_keys);
     }
 }
 
