@@ -871,7 +871,9 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
 // Measured alternatives that did not win at k = 8, m = 8, n = 2^26 (0.409 ms here): two CTAs of 8+1
 // warps per SM (0.43-0.44 ms), 16+1 warps (0.42), query pairs held in registers (0.44, spills at
 // 12 warps), and per-warp private rings without a producer warp (each warp fetching its own 4 KB
-// slice: 0.407 ms at 16 warps, but 3-4% slower at k = 3 and k = 16).
+// slice: 0.407 ms at 16 warps, but 3-4% slower at k = 3 and k = 16), and walking the passes of a
+// many-query launch inside the CTA without draining the ring (grid.y = 1): the extra loop level cost
+// the hot loop 8% at one pass and gained nothing at 13.
 // Tile t of the reference set goes to CTA t % gridDim.x (persistent grid); the ragged end of the set
 // (n % TILE_REFS references) is read with plain loads by the CTA whose turn it is.
 // =============================================================================================
