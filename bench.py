@@ -12,14 +12,19 @@ one 2^20-reference shard of an N*2^20 reference set (weak scaling; the queries a
 which is how the path shards (v8, /root/reference/sources/src/core.cu:875-883).
 
 `value`  : pairs/s with inputs resident in HBM, timed with CUDA events per step on the launching
-           stream (max over ranks), L2 flushed between steps.
+           stream (max over ranks), L2 flushed between steps, one untimed priming step after the sync.
 `e2e`    : pairs/s through the reference-facing C-ABI call (nn_b200_search_host = the body of
            cudaCallback) with pinned HOST buffers: H2D of queries+references, search, merge, D2H of
            the indices, all inside the timed region (wall clock; the call is synchronous).
-`roofline`: 3*k FP32 lane-ops per pair against the FP32 issue peak (nominal SMs*128*max clock and
-           the rate measured live with non-fused FADD/FMUL), plus n*k*4 reference bytes vs HBM.
+           `e2e.resident_index`: the same call against nn_b200_index_search (references already in HBM).
+`roofline`: the dominant kernel against the SLOWER of the two bounds north_star names -- 3*k FP32
+           lane-ops per pair at SMs*128*max clock (also measured live with non-fused FADD/FMUL) and
+           n*k*4 reference bytes at the measured HBM copy bandwidth; `traffic` = DRAM bytes of that
+           kernel from the committed ncu capture (profiles/traffic.json).
 `cpu_baseline`: the reference's own v0 (oracle/_ref, built with its -Ofast flags) -- or the oracle
            port where /root/reference was never available -- on a bounded query sample.
+--workload cfg1..cfg5 selects another BASELINE config; --scaling strong shards the workload's n
+over the ranks instead of giving every rank n references.
 """
 from __future__ import annotations
 
