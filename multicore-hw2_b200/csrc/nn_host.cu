@@ -288,7 +288,7 @@ static double qreg_model_cycles(int k, int q, int occ, int sms, int64_t m, int64
     const int64_t qtiles = (m + 128 * (int64_t)q - 1) / (128 * (int64_t)q);
     const int64_t total = qtiles * splits;
     int64_t rps = (n + splits - 1) / splits;
-    rps = (rps + 3) / 4 * 4;
+    rps = (rps + 7) / 8 * 8; // whole chunks (4 points; 8 in the NN_QREG_CH8 build) and 16-byte aligned starts
     if (rps_out)
         *rps_out = rps;
     // f_q: measured pipe share of the tile shape itself (shared loads and compares per packed

@@ -68,6 +68,9 @@
 #ifndef NN_QREG_UNROLL_NARROW
 #define NN_QREG_UNROLL_NARROW 1 // unroll the chunk loop 2x (Q = 4) / 4x (Q <= 2): -10% at Q = 1 and at k = 16, m = 1024; +-1% elsewhere
 #endif
+#ifndef NN_QREG_CH8
+#define NN_QREG_CH8 1 // 8-point chunks at k = 3 (fewer compares and selects per pair): +1..4% there, -0.4% at k = 4
+#endif
 #ifndef NN_QREG_PREFETCH
 #define NN_QREG_PREFETCH 1 // query-register kernel: load the next reference group while computing the current one
 #endif
@@ -274,7 +277,7 @@ struct QregDefault
 template <int K>
 struct QregCfg
 {
-    static constexpr int CH = 4;                                // references per chunk
+    static constexpr int CH = (NN_QREG_CH8 && K == 3) ? 8 : 4;  // references per chunk
     static constexpr int TR = ((2048 / K) / 8) * 8;             // references per tile (~8 KB)
     static constexpr int STAGES = 3;
     static constexpr int TILE_FLOATS = TR * K;
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
     const int tid = threadIdx.x;
     const uint32_t split = blockIdx.x % a.splits;
     const uint32_t qtile = blockIdx.x / a.splits;
-    // This CTA's references: [r0, r1).  r0 is a multiple of CH (= 4 points, 16-byte aligned for every
+    // This CTA's references: [r0, r1).  r0 is a multiple of 8 points (a whole chunk, 16-byte aligned for every
     // k); whole chunks [r0, r1c) stream through the TMA ring in tiles of up to TR points, and the
     // ragged end of the reference set (< CH points, last split only) is handled after the loop.
     const uint32_t r0 = min(split * a.refs_per_split, a.n);
