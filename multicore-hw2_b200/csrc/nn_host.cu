@@ -293,7 +293,14 @@ static double qreg_model_cycles(int k, int q, int occ, int sms, int64_t m, int64
         *rps_out = rps;
     // f_q: measured pipe share of the tile shape itself (shared loads and compares per packed
     // instruction grow as the tile narrows; one query per thread cannot use the pair-packed math)
-    const double f_q = q >= 8 ? 1.0 : (q >= 4 ? 0.988 : (q >= 2 ? 0.965 : 1.0 / 1.3));
+    double f_q = q >= 8 ? 1.0 : (q >= 4 ? 0.988 : (q >= 2 ? 0.965 : 1.0 / 1.3));
+    // measured at m = 16384, n = 2^19 on B200 (fraction of the FP32 roofline) where 8 and 4 queries per
+    // thread are both built: the 8-wide tile runs at 128 registers and loses to the 4-wide one at
+    // k = 5, 7, 8
+    static const double share8[9] = {0, 0, 0, 0.993, 0.985, 0.941, 0.954, 0.949, 0.924};
+    static const double share4[9] = {0, 0, 0, 0.974, 0.975, 0.973, 0.943, 0.960, 0.954};
+    if (k <= 8 && q >= 2)
+        f_q = (q == 8 ? share8[k] : (q == 4 ? share4[k] : share4[k] * 0.975)) / 0.993;
     const double cpr = (q >= 2 ? (q / 2) * (3.0 * k - 1.0) * 2.0 : (3.0 * k - 1.0)) / f_q;
     auto eff = [](int64_t c) { return c <= 1 ? 0.58 : (c == 2 ? 0.78 : (c == 3 ? 0.86 : 0.92)); };
     // Per-CTA prologue (query loads) and epilogue (re-read of the Q winning 4-point chunks): every
