@@ -157,6 +157,11 @@ NN_B200_API int nn_b200_probe_fp32(int mode, int iters, double *lane_ops_per_s);
  * grid); written into buf (NUL-terminated, truncated to len). */
 NN_B200_API int nn_b200_describe_plan(int k, int m, int64_t n, char *buf, size_t len);
 
+/* Which kernel family nn_b200_nearest_keys picks for m queries x n references of k dimensions (pure
+ * arithmetic, no device needed): 1 query-register, 2 reference-register, 4 reference-stream;
+ * NN_B200_EINVAL for a bad shape. */
+NN_B200_API int nn_b200_plan_variant(int k, int m, int64_t n);
+
 /* Introspection of the launch planner (pure arithmetic, no device needed): for the query-register
  * kernel with `q` queries per thread (tile = 128 q queries) at `occ` CTAs per SM on `sms` SMs, how
  * many reference splits per query tile a search of m queries x n references is launched with and

@@ -42,6 +42,7 @@ SIGNATURES = {
     "nn_b200_index_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int)]),
     "nn_b200_index_destroy": (None, [ctypes.c_void_p]),
     "nn_b200_warmup": (ctypes.c_int, []),
+    "nn_b200_plan_variant": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64]),
     "nn_b200_describe_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_char_p, ctypes.c_size_t]),
 }
 CXX_SYMBOL = "_Z12cudaCallbackiiiPfS_PPi"  # ::cudaCallback(int,int,int,float*,float*,int**), core.h:71

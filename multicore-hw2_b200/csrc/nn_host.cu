@@ -264,6 +264,11 @@ static int dev_info(int dev, DevInfo *out)
 // ---------------------------------------------------------------------------------------------
 // launch planning
 // ---------------------------------------------------------------------------------------------
+static bool check_shape_quiet(int k, int m, int64_t n)
+{
+    return k < NN_B200_KMIN || k > NN_B200_KMAX || m < 0 || n < 0 || n > 0x7fffffffLL;
+}
+
 struct Plan
 {
     int variant = 0; // 1 qreg, 2 rreg, 3 plain, 4 rtma
@@ -371,6 +376,32 @@ extern "C" int nn_b200_plan_splits(int k, int q, int occ, int sms, int64_t m, in
     return NN_B200_OK;
 }
 
+// Which kernel family searches m queries against n references (pure arithmetic).
+//   m <= 4: purely HBM-bound, plain register loads stream fastest (6.9 TB/s)  -> 2, reference-register
+//   m > rreg_max_m (112): the 128-query tiles are full enough                  -> 1, query-register
+//   between them the reference-stream kernel re-streams the set once per pass of 8 queries and pays
+//   ~7.5 us of pipeline fill, merge and drain per pass, while the query-register kernel streams it
+//   once but computes on a 128-query tile however few queries there are.  Fitted to the B200 sweeps
+//   of profiles/README.md (k = 3, 8, 16; m = 8, 32, 100; n = 2^16 .. 2^24), in microseconds:
+//     t_stream = 5 + passes * (7.5 + 0.787 * n*k / 1e6)     t_tile = 4 + 13.8 * n*k / 1e6
+static int auto_variant(int k, int m, int64_t n)
+{
+    if (m <= 4)
+        return 2;
+    if (m > g_opt.rreg_max_m.load())
+        return 1;
+    const double x = (double)n * k * 1e-6, passes = (double)((m + 7) / 8);
+    const double t_stream = 5.0 + passes * (7.5 + 0.787 * x), t_tile = 4.0 + 13.8 * x;
+    return t_stream < t_tile ? 4 : 1;
+}
+
+extern "C" int nn_b200_plan_variant(int k, int m, int64_t n)
+{
+    if (check_shape_quiet(k, m, n))
+        return NN_B200_EINVAL;
+    return auto_variant(k, m, n);
+}
+
 static int make_plan_uncached(int k, int m, int64_t n, bool soa, const DevInfo &di, Plan *p)
 {
     int variant = (int)g_opt.variant.load();
@@ -380,24 +411,8 @@ static int make_plan_uncached(int k, int m, int64_t n, bool soa, const DevInfo &
     // search is purely HBM-bound and plain register loads stream fastest (6.9 TB/s); from 5 queries
     // on the FP32 pipe matters as well and the TMA-ring kernel wins at every k (B200 sweeps in
     // profiles/); beyond ~112 queries the query-register kernel's 128-query tile is full enough.
-    // Between them, 5..112 queries: the reference-stream kernel re-streams the set once per pass of 8
-    // queries and pays ~7.5 us of pipeline fill, merge and drain per pass, the query-register kernel
-    // streams it once but computes on a 128-query tile however few queries there are.  Fitted to the
-    // B200 sweeps of profiles/README.md (k = 3, 8, 16; m = 8, 32, 100; n = 2^16 .. 2^24), microseconds:
-    //   t_stream = 5 + passes * (7.5 + 0.787 * n*k / 1e6)     t_tile = 4 + 13.8 * n*k / 1e6
     if (variant == 0)
-    {
-        if (m <= 4)
-            variant = 2;
-        else if (m <= g_opt.rreg_max_m.load())
-        {
-            const double x = (double)n * k * 1e-6, passes = (double)((m + 7) / 8);
-            const double t_stream = 5.0 + passes * (7.5 + 0.787 * x), t_tile = 4.0 + 13.8 * x;
-            variant = t_stream < t_tile ? 4 : 1;
-        }
-        else
-            variant = 1;
-    }
+        variant = auto_variant(k, m, n);
     p->variant = variant;
     if (variant == 1)
     {

@@ -154,3 +154,27 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+
+
+def test_kernel_family_selection_rule(nn):
+    """nn_b200_plan_variant (pure arithmetic): reference-register kernel up to 4 queries,
+    query-register kernel above 112, and between them the fitted time model -- checked against the
+    B200 sweep it was fitted on (profiles/r01_fewquery_crossover.json): the pick may never cost more
+    than 15% over the faster kernel, and must be the faster one in at least 33 of the 36 cases."""
+    import json
+    L = nn.lib()
+    assert L.nn_b200_plan_variant(8, 1, 1 << 26) == 2 and L.nn_b200_plan_variant(16, 4, 100) == 2
+    assert L.nn_b200_plan_variant(8, 8, 1 << 26) == 4            # BASELINE config 3
+    assert L.nn_b200_plan_variant(16, 4096, 1 << 20) == 1 and L.nn_b200_plan_variant(3, 113, 1 << 26) == 1
+    assert L.nn_b200_plan_variant(2, 8, 8) == nn._lib.EINVAL if hasattr(nn, "_lib") else True
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rows = json.load(open(os.path.join(root, "profiles", "r01_fewquery_crossover.json")))["rows"]
+    good = 0
+    for r in rows:
+        pick = L.nn_b200_plan_variant(r["k"], r["m"], r["n"])
+        assert pick in (1, 4)
+        got = r["qreg_us"] if pick == 1 else r["rtma_us"]
+        best = min(r["qreg_us"], r["rtma_us"])
+        assert got <= 1.15 * best, r
+        good += got <= 1.02 * best
+    assert len(rows) == 36 and good >= 33, good
