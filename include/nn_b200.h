@@ -111,7 +111,10 @@ typedef struct nn_b200_index nn_b200_index;
 
 /* Uploads the n references (host, AoS [n][k]) to num_gpus devices (<= 0: all visible). */
 NN_B200_API int nn_b200_index_create(int k, int n, const float *referencePoints, int num_gpus, nn_b200_index **index);
-/* results[i] = index of the nearest resident reference of query i (m queries, host, AoS [m][k]). */
+/* results[i] = index of the nearest resident reference of query i (m queries, host, AoS [m][k]).
+ * On a single-GPU index, batches of up to 1 MiB of queries are launch-bound: their copy-in, init,
+ * search, unpack and copy-out are captured once per batch size into a CUDA graph and replayed with
+ * one launch (option "index_graph" = 0 disables). */
 NN_B200_API int nn_b200_index_search(nn_b200_index *index, int m, const float *searchPoints, int *results);
 NN_B200_API int nn_b200_index_info(const nn_b200_index *index, int *k, int64_t *n, int *gpus);
 NN_B200_API void nn_b200_index_destroy(nn_b200_index *index);

@@ -147,11 +147,14 @@ def test_resident_index_build_once_query_many(nn, oracle):
     S, R = cases.make("duplicated", 4711, 6, 300, 70001)
     want = oracle.v0(S, R, threads=0)
     for gpus in sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()}):
-        with nn.Index(R, num_gpus=gpus) as ix:
-            assert (ix.k, ix.n, ix.gpus) == (6, 70001, gpus)
-            for lo, hi in [(0, 1), (1, 8), (0, 300), (293, 300)]:
-                assert np.array_equal(ix.search(S[lo:hi]), want[lo:hi]), (gpus, lo, hi)
-            assert ix.search(S[:0]).size == 0
+        for graph in (1, 0):  # small batches on one GPU replay a captured CUDA graph; 0 = plain enqueues
+            nn.set_option("index_graph", graph)
+            with nn.Index(R, num_gpus=gpus) as ix:
+                assert (ix.k, ix.n, ix.gpus) == (6, 70001, gpus)
+                for lo, hi in [(0, 1), (1, 8), (0, 300), (293, 300), (0, 1), (1, 8)]:  # repeats replay the graph
+                    assert np.array_equal(ix.search(S[lo:hi]), want[lo:hi]), (gpus, graph, lo, hi)
+                assert ix.search(S[:0]).size == 0
+    nn.set_option("index_graph", 1)
     with nn.Index(np.zeros((0, 3), np.float32), k=3) as ix:   # empty index: v0's start state, index 0
         assert ix.search(np.ones((4, 3), np.float32)).tolist() == [0] * 4
     with pytest.raises(nn.NNError):
