@@ -204,7 +204,31 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries print to stdout on their own (NCCL's version banner under torchrun).  The contract is ONE
+    JSON line on stdout: everything else written to file descriptor 1 during the run is sent to
+    stderr, and emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -221,6 +245,7 @@ def main():
                          "workload's n references are sharded over the ranks (BASELINE configs[3] at 1/2/4/8 GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    _quiet_stdout()
 
     if args.impl == "reference":
         return run_reference(args)
@@ -464,7 +489,7 @@ def main():
             "merge_ms": sum(merge_ms) / len(merge_ms),
             "kernel_ms_min_max_over_ranks": [float(kern_lo.item()), float(kern_hi.item())],
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
