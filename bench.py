@@ -1,34 +1,44 @@
 #!/usr/bin/env python
 """bench.py -- contract benchmark of the brute-force 1-NN path (BASELINE.json metric: query.ref
-pairs/s and ms/call).
+pairs/s and ms/call at 1/2/4/8 B200 vs roofline, v0 CPU baseline beside it).
 
     python bench.py --gpus N --steps K --warmup W              # our arm (CUDA, libnn_b200.so)
     python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU v0 on the host cores
 
-Workload (config.workload): BASELINE.json configs[1] = k=16, m=4096 queries, n=1,048,576
-references per GPU.  One "step" = one complete search: keys_init -> fused distance+argmin ->
-[all-reduce(min) of packed keys over NCCL when N > 1] -> keys_unpack.  With N GPUs every rank owns
-one 2^20-reference shard of an N*2^20 reference set (weak scaling; the queries are replicated),
-which is how the path shards (v8, /root/reference/sources/src/core.cu:875-883).
+Workload (config.workload): BASELINE configs[3] = k=16, m=65,536 queries, n=16,777,216 references --
+the configuration `north_star` quotes the 1/2/4/8-GPU metric on; it fits one GPU (1 GiB of
+references).  With N GPUs the ONE reference set is sharded over the ranks (strong scaling, v8's job:
+/root/reference/sources/src/core.cu:875-883) and the per-query packed keys are merged with one
+all-reduce(min, u64) over NCCL.  --workload cfg1..cfg5 / --scaling weak select other runs.
 
-`value`  : pairs/s with inputs resident in HBM, timed with CUDA events per step on the launching
-           stream (max over ranks), L2 flushed between steps, one untimed priming step after the sync.
-`e2e`    : pairs/s through the reference-facing C-ABI call (nn_b200_search_host = the body of
-           cudaCallback) with pinned HOST buffers: H2D of queries+references, search, merge, D2H of
-           the indices, all inside the timed region (wall clock; the call is synchronous).
-           `e2e.resident_index`: the same call against nn_b200_index_search (references already in HBM).
-`roofline`: the dominant kernel against the SLOWER of the two bounds north_star names -- 3*k FP32
-           lane-ops per pair at SMs*128*max clock (also measured live with non-fused FADD/FMUL) and
-           n*k*4 reference bytes at the measured HBM copy bandwidth; `traffic` = DRAM bytes of that
-           kernel from the committed ncu capture (profiles/traffic.json).
-`cpu_baseline`: the reference's own v0 (oracle/_ref, built with its -Ofast flags) -- or the oracle
-           port where /root/reference was never available -- on a bounded query sample.
---workload cfg1..cfg5 selects another BASELINE config; --scaling strong shards the workload's n
-over the ranks instead of giving every rank n references.
+One "step" = one complete search with inputs resident in HBM:
+  N = 1: ONE kernel launch (nn_b200_search_device: distance + argmin + merge + index store);
+  N > 1: search (packed keys out) -> all-reduce(min) -> keys_unpack.
+
+`value`   : pairs/s (m * n_total / step time), CUDA events per step on the launching stream, summed over
+            the K steps, max over ranks; L2 flushed between steps.
+`e2e`     : the same metric through the reference-facing entry point `cudaCallback` with malloc'ed
+            (pageable) HOST arrays, exactly what the reference's harness passes and times
+            (main.cu:69-73, generator.h:37/44): H2D + search + merge + D2H + malloc inside the timed
+            region, rank 0 driving all N GPUs in one process as v8 does.  `e2e.pinned` is the same call
+            (error-code variant) with pinned buffers, `e2e.resident_index` the build-once/query-many API.
+`roofline`: the fused search kernel against the SLOWER of the two bounds north_star names -- 3k FP32
+            lane-ops per pair at SMs*128*max clock and n*k*4 reference bytes at the measured HBM copy
+            bandwidth; kernel time from CUDA events around the launch; `traffic` from the committed ncu
+            capture (profiles/traffic.json).
+`parity_spot_check`: 16 queries of the measured result re-computed by the CPU oracle (v0 restatement)
+            against the full reference set -- at every N, for the device-resident result (NCCL merge)
+            and for cudaCallback's (in-kernel NVLink merge), plus the in-process NCCL merge at N > 1.
+`all_configs` (N = 1): a short device-resident + e2e + oracle-checked leg for each of the other BASELINE
+            configs, so that every config has a driver-visible roofline fraction.
+`cpu_baseline`: the reference's own v0 (oracle/_ref, built with its -Ofast flags; the oracle port where
+            /root/reference was never available) on a bounded query sample, all host threads
+            (CPU affinity count, not OMP_NUM_THREADS) -- and the 1-thread figure, which is what v0 is.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -40,22 +50,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (k, m, n per GPU)
-    "cfg2": (16, 4096, 1 << 20),
+    # name: (k, m, n)
     "cfg1": (3, 1024, 65536),
+    "cfg2": (16, 4096, 1 << 20),
     "cfg3": (8, 8, 1 << 26),
     "cfg4": (16, 65536, 1 << 24),
     "cfg5": (3, 1 << 20, 1 << 20),
 }
 DESCR = {
-    "cfg2": "BASELINE configs[1]: k=16, m=4096 queries, n=1,048,576 refs per GPU",
-    "cfg1": "BASELINE configs[0]: k=3, m=1024, n=65536",
-    "cfg3": "BASELINE configs[2]: k=8, m=8, n=67,108,864 per GPU",
-    "cfg4": "BASELINE configs[3]: k=16, m=65536, n=16,777,216 per GPU",
-    "cfg5": "BASELINE configs[4]: k=3, m=1,048,576, n=1,048,576 per GPU",
+    "cfg1": "BASELINE configs[0]: k=3, m=1,024 queries, n=65,536 refs (TA sample 6 shape)",
+    "cfg2": "BASELINE configs[1]: k=16, m=4,096 queries, n=1,048,576 refs",
+    "cfg3": "BASELINE configs[2]: k=8, m=8 queries, n=67,108,864 refs",
+    "cfg4": "BASELINE configs[3]: k=16, m=65,536 queries, n=16,777,216 refs, reference shards over the GPUs",
+    "cfg5": "BASELINE configs[4]: k=3, m=1,048,576 queries, n=1,048,576 refs",
 }
 METRIC = "query*ref pairs/s (brute-force 1-NN, bit-exact vs v0)"
 UNIT = "pairs/s"
+
+
+def workload_string(name: str, scaling: str, world: int) -> str:
+    """Identical for both arms and -- under strong scaling -- for every N."""
+    if scaling == "weak" and world > 1:
+        return DESCR[name] + f" PER GPU (weak scaling, x{world})"
+    return DESCR[name]
 
 
 def measured_peaks():
@@ -122,41 +139,71 @@ class ClockSampler:
 
 
 def host_cores() -> int:
+    """Host threads this process may use: its CPU affinity, NOT OMP_NUM_THREADS (torchrun sets that to 1)."""
     try:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
 
 
-def cpu_arm(k, m, n, S, R, budget_s=12.0):
+# ---------------------------------------------------------------------------------------------------
+# CPU arm (the only place, besides the parity spot checks, where oracle/ is executed)
+# ---------------------------------------------------------------------------------------------------
+def cpu_arm(k, m, n, S, R, budget_s=12.0, one_thread=True):
     """Times the reference's CPU implementation (v0) on a bounded sample of the workload's queries
-    against the FULL reference set, all host threads.  Returns the cpu_baseline dict."""
+    against the FULL reference set on all host threads (and once on one thread).  Returns the
+    cpu_baseline dict."""
     from oracle import oracle
-    import numpy as np
     cores = host_cores()
     use_ref = oracle.ref_available(fast=True)
     kind = "reference" if use_ref else "port"
 
-    def run(q):
+    def run(q, threads):
         t0 = time.perf_counter()
         if use_ref:
-            _, used = oracle.ref_v0(S[:q], R, k, threads=0, fast=True)
+            _, used = oracle.ref_v0(S[:q], R, k, threads=threads, fast=True)
         else:
-            oracle.v0(S[:q], R, k, threads=0)
-            used = min(cores, q)
+            oracle.v0(S[:q], R, k, threads=threads)
+            used = min(threads, q)
         return time.perf_counter() - t0, used
 
     probe_q = max(1, min(m, cores))
-    t_probe, used = run(probe_q)  # also warms the pages
+    t_probe, used = run(probe_q, cores)  # also warms the pages
     rate = probe_q * n / max(t_probe, 1e-9)
     q = int(max(probe_q, min(m, (budget_s * rate / n) // max(1, cores) * max(1, cores))))
     q = max(1, min(q, m))
-    t, used = run(q)
-    return {"value": q * n / t, "unit": UNIT, "cores": used, "kind": kind,
-            "sample": f"first {q} of {m} queries x all {n} references, k={k}, {t:.2f} s; "
-                      f"{'oracle/_ref = reference v0 (core.cu:25-63) built -Ofast' if use_ref else 'oracle/nn_oracle.c port, -O2 -ffp-contract=off'}"
-                      f", queries split over {used} host threads",
-            "seconds": t}
+    t, used = run(q, cores)
+    out = {"value": q * n / t, "unit": UNIT, "cores": used, "kind": kind,
+           "sample": f"first {q} of {m} queries x all {n} references, k={k}, {t:.2f} s; "
+                     f"{'oracle/_ref = reference v0 (core.cu:25-63) built -Ofast' if use_ref else 'oracle/nn_oracle.c port, -O2 -ffp-contract=off'}"
+                     f", queries split over {used} host threads (CPU affinity count; OMP_NUM_THREADS ignored)",
+           "seconds": t}
+    if one_thread:
+        q1 = max(1, min(m, int(q / max(1, used) / 4) or 1))
+        t1, _ = run(q1, 1)
+        out["value_1_thread"] = q1 * n / t1
+        out["sample_1_thread"] = f"first {q1} queries, 1 thread (v0 as written: serial, core.cu:27-62), {t1:.2f} s"
+    return out
+
+
+def reference_gpu_leg():
+    """The reference's OWN CUDA path (core.cu recompiled for sm_100a, oracle/_ref/libref_gpu.so) timed on
+    this B200 on TA samples 6 and 7 -- the shapes on which it is valid (v8 -> v7, core.cu:871-872);
+    sample 6 is BASELINE config 1.  Runs in a subprocess (static initialisers, thrust aborts)."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "ref_gpu_time.py")
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_gpu.so")):
+        return {"unavailable": "oracle/_ref/libref_gpu.so not built (needs /root/reference at build time)"}
+    try:
+        env = dict(os.environ)
+        env.pop("NN_B200_GPUS", None)
+        r = subprocess.run([sys.executable, exe, "6", "7"], capture_output=True, text=True, timeout=180, env=env)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"unavailable": f"rc={r.returncode}: {(r.stderr or r.stdout)[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:  # a baseline beside the number, never fatal
+        return {"unavailable": str(e)[:300]}
 
 
 def make_inputs(k, m, n, seed, device):
@@ -170,21 +217,21 @@ def make_inputs(k, m, n, seed, device):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path (v0) on this box's host cores."""
+    """--impl reference: the reference's own CPU path (v0) on this box's host cores, same config."""
     import numpy as np
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    k, m, n1 = WORKLOADS[args.workload]
-    n = n1 * args.gpus
+    world = args.gpus
+    k, m, n = WORKLOADS[args.workload]
+    n_total = n * world if args.scaling == "weak" else n
     rng = np.random.default_rng(1000)
     S = rng.random((m, k), dtype=np.float32)
-    R = rng.random((n, k), dtype=np.float32)
+    R = rng.random((n_total, k), dtype=np.float32)
     per_step_budget = max(1.0, min(8.0, 150.0 / max(1, args.steps + args.warmup)))
-    res = None
     vals = []
     for i in range(args.warmup + args.steps):
-        res = cpu_arm(k, m, n, S, R, budget_s=per_step_budget)
+        res = cpu_arm(k, m, n_total, S, R, budget_s=per_step_budget, one_thread=(i == args.warmup + args.steps - 1))
         if i >= args.warmup:
             vals.append(res)
     tot_pairs = sum(v["value"] * v["seconds"] for v in vals)
@@ -196,10 +243,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, len(vals)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": DESCR[args.workload] + f" x {args.gpus} GPU shard(s)", "k": k, "m": m, "n": n,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(args.workload, args.scaling, world), "k": k, "m": m, "n_total": n_total,
                    "note": "CPU arm: every step is a bounded sample of the workload's queries against the full "
-                           "reference set; pairs/s = sample pairs / wall time"},
+                           "reference set; pairs/s = sample pairs / wall time; same thread count at every N"},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -231,18 +278,230 @@ def emit(line: dict) -> None:
         os.write(_REAL_STDOUT, data)
 
 
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+class L2Flush:
+    """256 MiB written, then another 256 MiB read, so that the 126 MB L2 holds neither the previous
+    step's references nor dirty lines whose write-back would ride on the timed kernel's HBM stream."""
+
+    def __init__(self, dev):
+        import torch
+        self.w = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.r = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
+
+    def __call__(self):
+        self.w.zero_()
+        self.r.sum()
+
+
+def roofline_of(k, m, n_local, kernel_ms, peaks, sms, plan, workload):
+    """north_star: the slower of 3k non-fused FP32 lane-ops per pair at the FP32 issue peak and
+    n*k*4 reference bytes at HBM bandwidth."""
+    kern_s = kernel_ms * 1e-3
+    ops = 3.0 * k * m * n_local
+    ref_bytes = float(n_local) * k * 4
+    fp32_peak = sms * 128 * peaks["sm_max_mhz"] * 1e6
+    hbm_peak = peaks["hbm_gbs"] * 1e9
+    t_fp32, t_hbm = ops / fp32_peak, ref_bytes / hbm_peak
+    kernel_name = {"qreg": "nn_qreg_kernel", "rreg": "nn_rreg_kernel", "rtma": "nn_rtma_kernel",
+                   "qflex": "nn_qflex_kernel"}.get(plan.split()[0], plan.split()[0])
+    fp32_part = {"achieved_tlops": ops / kern_s / 1e12, "peak_tlops": fp32_peak / 1e12, "frac": t_fp32 / kern_s,
+                 "bound_ms": t_fp32 * 1e3,
+                 "peak_source": f"{sms} SMs x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)"}
+    hbm_part = {"achieved_gbs": ref_bytes / kern_s / 1e9, "peak_gbs": peaks["hbm_gbs"], "frac": t_hbm / kern_s,
+                "bound_ms": t_hbm * 1e3, "peak_source": f"{peaks['source']} hbm_gbs (measured copy bandwidth)"}
+    if t_fp32 >= t_hbm:
+        roof = {"bound": "fp32", "kernel": kernel_name, "achieved": fp32_part["achieved_tlops"],
+                "peak": fp32_part["peak_tlops"], "unit": "TFLOP/s (non-fused FP32 lane-ops: 3k per pair)",
+                "frac": fp32_part["frac"]}
+    else:
+        roof = {"bound": "hbm", "kernel": kernel_name, "achieved": hbm_part["achieved_gbs"],
+                "peak": hbm_part["peak_gbs"], "unit": "GB/s", "frac": hbm_part["frac"]}
+    roof.update({"kernel_ms": kernel_ms, "fp32": fp32_part, "hbm": hbm_part,
+                 "algorithmic": {"lane_ops_per_launch": ops, "bytes_per_launch": ref_bytes},
+                 "traffic": None})
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(workload)
+        if t and t.get("kernel") == kernel_name:
+            roof["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+            roof["traffic_source"] = t["source"]
+    return roof
+
+
+def device_leg(nn, k, m, n_total, steps, warmup, dev, world=1, rank=0, scaling="strong", seed=1000, sampler=None):
+    """K timed steps of the device-resident search on this rank's shard.  Returns a dict of raw timings
+    plus the tensors (queries, shard, result) for the later legs."""
+    import torch
+    import torch.distributed as dist
+    from multicore_hw2_b200 import device, sharded
+    shard = sharded.ShardedSearch(n_total, rank, world)
+    begin, n_local = shard.begin, shard.count
+    S, _ = make_inputs(k, m, 4, seed, dev)
+    _, R = make_inputs(k, 4, max(n_local, 1), seed + 1000 + rank, dev)
+    R = R[:n_local]
+    ws = device.Workspace(m, dev)
+    out = torch.empty(m, dtype=torch.int32, device=dev)
+    keys = torch.empty(m, dtype=torch.int64, device=dev) if world > 1 else None
+    flush = L2Flush(dev)
+
+    def step(e0=None, e1=None, e2=None, e3=None):
+        if e0 is not None:
+            e0.record()
+        if world == 1:
+            device.search(S, R, ws, out=out, index_base=begin)          # ONE launch
+        else:
+            device.search(S, R, ws, keys_out=keys, index_base=begin)    # search -> final keys of this shard
+            if e1 is not None:
+                e1.record()
+            sharded.merge_keys(keys)                                     # all-reduce(min) over NCCL
+            if e2 is not None:
+                e2.record()
+            device.keys_unpack(keys, out)
+        if e3 is not None:
+            e3.record()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.start()
+    gc.disable()
+    # one more untimed step AFTER the synchronize, so that the host is enqueueing ahead of the device
+    # when the first timed step starts (right after a host sync every launch latency of the first
+    # step would be exposed)
+    flush()
+    step()
+    launches0 = nn.launch_count()
+    t_wall0 = time.perf_counter()
+    for i in range(steps):
+        flush()  # outside the per-step event window
+        step(*ev[i])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    gc.enable()
+    launches = nn.launch_count() - launches0
+    step_ms = [e[0].elapsed_time(e[3]) for e in ev]
+    if world == 1:
+        kern_ms, merge_ms = list(step_ms), [0.0] * steps
+    else:
+        kern_ms = [e[0].elapsed_time(e[1]) for e in ev]
+        merge_ms = [e[1].elapsed_time(e[2]) for e in ev]  # incl. waiting for the slowest rank
+    return {"S": S, "R": R, "out": out, "begin": begin, "n_local": n_local, "step_ms": step_ms, "kern_ms": kern_ms,
+            "merge_ms": merge_ms, "launches": launches, "wall_s": t_wall,
+            "plan": nn.describe_plan(k, m, max(n_local, 1))}
+
+
+def e2e_leg(nn, k, m, n_total, Sh, Rh, calls, world, full=True):
+    """End to end through the host entry points, rank 0 driving `world` GPUs in one process.
+    Sh, Rh: pageable numpy arrays (malloc'ed memory, as the reference's harness passes)."""
+    import numpy as np
+    import torch
+    pairs = float(m) * float(n_total)
+    os.environ["NN_B200_GPUS"] = str(world)   # cudaCallback has no GPU-count argument (core.h:71)
+
+    def timed(fn, reps):
+        fn()
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        return (time.perf_counter() - t0) / reps, r
+
+    t_cb, res = timed(lambda: nn.cudaCallback(k, m, n_total, Sh, Rh), calls)
+    bytes_in, bytes_out = int((m * k + n_total * k) * 4), int(m * 4)
+    e2e = {"value": pairs / t_cb, "unit": UNIT, "ms_per_call": t_cb * 1e3, "calls_timed": calls,
+           "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
+           "api": "cudaCallback(k, m, n, searchPoints, referencePoints, &results) -- the reference's entry point "
+                  "(core.h:71), malloc'ed pageable host arrays as main.cu:69-73 times it; wall clock around the "
+                  f"call incl. the malloc of the result; {world} GPU(s) driven from one process"}
+    results = {"cudaCallback": res}
+    if full:
+        Sp, Rp = torch.from_numpy(Sh).pin_memory(), torch.from_numpy(Rh).pin_memory()
+        buf = np.empty(m, dtype=np.int32)
+        t_pin, _ = timed(lambda: nn.search_host(Sp, Rp, k, num_gpus=world, out=buf), calls)
+        results["search_host_pinned"] = buf.copy()
+        e2e["pinned"] = {"value": pairs / t_pin, "unit": UNIT, "ms_per_call": t_pin * 1e3,
+                         "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
+                         "api": "nn_b200_search_host (same body, error code instead of exit), PINNED host buffers"}
+        if world > 1:
+            nn.set_option("p2p_merge", 0)
+            try:
+                buf2 = np.empty(m, dtype=np.int32)
+                t_nccl, _ = timed(lambda: nn.search_host(Sp, Rp, k, num_gpus=world, out=buf2), min(calls, 3))
+                results["search_host_nccl"] = buf2
+                e2e["pinned_nccl_merge"] = {"ms_per_call": t_nccl * 1e3,
+                                            "api": "same with option p2p_merge=0: in-process ncclAllReduce(min, u64)"}
+            finally:
+                nn.set_option("p2p_merge", 1)
+        with nn.Index(Rp, k, num_gpus=world) as ix:
+            buf3 = np.empty(m, dtype=np.int32)
+            t_ix, _ = timed(lambda: ix.search(Sp, out=buf3), calls)
+        results["index"] = buf3
+        e2e["resident_index"] = {"value": pairs / t_ix, "unit": UNIT, "ms_per_call": t_ix * 1e3,
+                                 "h2d_bytes_per_step": int(m * k * 4), "d2h_bytes_per_step": bytes_out,
+                                 "api": "nn_b200_index_search (references resident in HBM, build once / query many)"}
+        del Sp, Rp
+    return e2e, results
+
+
+def spot_check(k, m, Sh, Rh, results: dict, nq=16):
+    """`nq` evenly spaced queries re-computed by the CPU oracle against the FULL reference set and
+    compared with every result array given.  Returns (dict name -> bool, rows)."""
+    import numpy as np
+    from oracle import oracle
+    rows = np.unique(np.linspace(0, m - 1, num=min(nq, m)).astype(np.int64))
+    want = oracle.v0(np.ascontiguousarray(Sh[rows]), Rh, k, threads=host_cores())
+    return {name: bool(np.array_equal(np.asarray(r)[rows], want)) for name, r in results.items()}, len(rows)
+
+
+def gather_references(R, world, rank, host_group):
+    """All shards on rank 0's host as ONE pageable numpy array (None elsewhere)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return R.cpu().numpy()
+    counts = [torch.zeros(1, dtype=torch.int64, device=R.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([R.shape[0]], dtype=torch.int64, device=R.device))
+    counts = [int(c.item()) for c in counts]
+    cap = max(counts)
+    pad = torch.zeros((cap, R.shape[1]), dtype=R.dtype, device=R.device)
+    pad[:R.shape[0]] = R
+    gathered = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, gathered, dst=0)
+    torch.cuda.synchronize()
+    out = None
+    if rank == 0:
+        out = np.concatenate([g[:c].cpu().numpy() for g, c in zip(gathered, counts)])
+        del gathered
+    del pad
+    torch.cuda.empty_cache()
+    dist.barrier(group=host_group)  # the other ranks now wait on the CPU, their GPUs are idle
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (contract default): every rank owns the workload's n references; strong: the "
-                         "workload's n references are sharded over the ranks (BASELINE configs[3] at 1/2/4/8 GPUs)")
+    ap.add_argument("--no-all-configs", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (contract default): the workload's ONE reference set is sharded over the ranks "
+                         "(v8, core.cu:875-883); weak: every rank owns the workload's n references")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     _quiet_stdout()
@@ -254,7 +513,6 @@ def main():
     import torch
     import torch.distributed as dist
     import multicore_hw2_b200 as nn
-    from multicore_hw2_b200 import device, sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -275,186 +533,57 @@ def main():
         # a spinning kernel on every other GPU, and rank 0's e2e call drives those GPUs itself
         host_group = dist.new_group(backend="gloo")
     nn.lib()
-
-    k, m, n_local = WORKLOADS[args.workload]
-    n_total = n_local * world
-    if args.scaling == "strong":
-        n_total = n_local
-        n_local = sharded.ShardedSearch(n_total, rank, world).count
     peaks = measured_peaks()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
 
-    # ---- inputs: queries replicated, this rank's reference shard; resident in HBM ----------------
-    S, _ = make_inputs(k, m, 4, 1000, dev)
-    _, R = make_inputs(k, 4, n_local, 2000 + rank, dev)
-    shard = sharded.ShardedSearch(n_total, rank, world)
-    # weak scaling keeps the per-rank shard at exactly the workload's n references
-    begin = shard.begin
-    assert shard.count == n_local and (args.scaling == "strong" or begin == rank * n_local)
-    keys = device.new_keys(m, dev)
-    out = torch.empty(m, dtype=torch.int32, device=dev)
-    # L2 flush between steps: 256 MiB written, then another 256 MiB read, so that the 126 MB L2 holds
-    # neither the previous step's references nor dirty lines whose write-back would ride on the
-    # timed kernel's HBM stream
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
+    k, m, n_wl = WORKLOADS[args.workload]
+    n_total = n_wl * world if args.scaling == "weak" else n_wl
 
-    def l2_flush():
-        flush.zero_()
-        flush_rd.sum()
-
-    def step():
-        device.keys_init(keys)
-        device.nearest_keys(S, R, keys, begin)
-        sharded.merge_keys(keys)
-        device.keys_unpack(keys, out)
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    mev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    # clocks are sampled on rank 0 only: NVML queries take driver locks, and with one poller per rank
-    # they delayed launches enough to show up as all-reduce skew (0.20 ms -> 0.05 ms per step at N = 8)
-    sampler = ClockSampler(local if rank == 0 else -1).start()
-    import gc
-    gc.disable()
-    # one more untimed step AFTER the synchronize, so that the host is enqueueing ahead of the device
-    # when the first timed step starts (right after a host sync every launch latency of the first
-    # step would be exposed: it measured 2-3x the others on the sub-millisecond workloads)
-    l2_flush()
-    step()
-    launches0 = nn.launch_count()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        l2_flush()  # outside the per-step event window
-        ev[i][0].record()
-        device.keys_init(keys)
-        kev[i][0].record()
-        device.nearest_keys(S, R, keys, begin)
-        kev[i][1].record()
-        sharded.merge_keys(keys)
-        mev[i].record()
-        device.keys_unpack(keys, out)
-        ev[i][1].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    gc.enable()
-    launches = nn.launch_count() - launches0
+    # ---- main leg: device-resident, K timed steps ------------------------------------------------
+    # clocks are sampled on rank 0 only: NVML queries take driver locks, and one poller per rank
+    # delayed launches enough to show up as all-reduce skew
+    sampler = ClockSampler(local if rank == 0 else -1)
+    leg = device_leg(nn, k, m, n_total, args.steps, args.warmup, dev, world, rank, args.scaling, sampler=sampler)
     clocks = sampler.stop()
-
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    kern_ms = [a.elapsed_time(b) for a, b in kev]
-    merge_ms = [kev[i][1].elapsed_time(mev[i]) for i in range(args.steps)]  # incl. waiting for the slowest rank
-    kern_all = torch.tensor([sum(kern_ms) / len(kern_ms)], dtype=torch.float64, device=dev)
-    kern_lo, kern_hi = kern_all.clone(), kern_all.clone()
+    step_ms, kern_ms, merge_ms = leg["step_ms"], leg["kern_ms"], leg["merge_ms"]
+    t = torch.tensor([sum(step_ms), sum(kern_ms) / len(kern_ms)], dtype=torch.float64, device=dev)
+    t_max, t_min = t.clone(), t.clone()
+    per_rank_steps = None
     if world > 1:
-        dist.all_reduce(kern_lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(kern_hi, op=dist.ReduceOp.MAX)
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
+        mine = torch.tensor(step_ms[:16], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank_steps = [[round(float(x), 4) for x in a.tolist()] for a in allr]
+    total_ms = float(t_max[0].item())
     ms_per_step = total_ms / args.steps
     pairs_per_step = float(m) * float(n_total)
     value = pairs_per_step / (ms_per_step * 1e-3)
-
-    # ---- roofline of the dominant kernel (this rank's fused distance+argmin launch) --------------
-    # north_star: the slower of 3k non-fused FP32 lane-ops per pair at the FP32 issue peak and
-    # n*k*4 reference bytes at HBM bandwidth.
     kern_ms_avg = sum(kern_ms) / len(kern_ms)
-    kern_s = kern_ms_avg * 1e-3
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    ops = 3.0 * k * m * n_local
-    ref_bytes = float(n_local) * k * 4
-    fp32_peak = sms * 128 * peaks["sm_max_mhz"] * 1e6
-    hbm_peak = peaks["hbm_gbs"] * 1e9
-    t_fp32, t_hbm = ops / fp32_peak, ref_bytes / hbm_peak
-    plan = nn.describe_plan(k, m, n_local)
-    kernel_name = {"qreg": "nn_qreg_kernel", "rreg": "nn_rreg_kernel", "rtma": "nn_rtma_kernel"}.get(plan.split()[0], plan.split()[0])
-    fp32_part = {"achieved_tlops": ops / kern_s / 1e12, "peak_tlops": fp32_peak / 1e12, "frac": t_fp32 / kern_s,
-                 "bound_ms": t_fp32 * 1e3,
-                 "peak_source": f"{sms} SMs x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)"}
-    hbm_part = {"achieved_gbs": ref_bytes / kern_s / 1e9, "peak_gbs": peaks["hbm_gbs"], "frac": t_hbm / kern_s,
-                "bound_ms": t_hbm * 1e3, "peak_source": f"{peaks['source']} hbm_gbs (measured copy bandwidth)"}
-    if t_fp32 >= t_hbm:
-        line_roof = {"bound": "fp32", "kernel": kernel_name, "achieved": fp32_part["achieved_tlops"],
-                     "peak": fp32_part["peak_tlops"], "unit": "TFLOP/s (non-fused FP32 lane-ops: 3k per pair)",
-                     "frac": fp32_part["frac"]}
-    else:
-        line_roof = {"bound": "hbm", "kernel": kernel_name, "achieved": hbm_part["achieved_gbs"],
-                     "peak": hbm_part["peak_gbs"], "unit": "GB/s", "frac": hbm_part["frac"]}
-    line_roof.update({"kernel_ms": kern_ms_avg, "fp32": fp32_part, "hbm": hbm_part,
-                      "algorithmic": {"lane_ops_per_launch": ops, "bytes_per_launch": ref_bytes},
-                      "traffic": None})
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        t = json.load(open(tpath)).get(args.workload)
-        if t and t.get("kernel") == kernel_name:
-            line_roof["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
-            line_roof["traffic_source"] = t["source"]
+    roof = roofline_of(k, m, leg["n_local"], kern_ms_avg, peaks, sms, leg["plan"], args.workload)
     if rank == 0:
         try:
-            meas = nn.probe_fp32(0)
-            meas2 = nn.probe_fp32(1)
-            line_roof["peak_measured"] = max(meas, meas2) / 1e12
-            line_roof["peak_measured_scalar"] = meas / 1e12
-            line_roof["peak_measured_f32x2"] = meas2 / 1e12
-            line_roof["frac_of_measured"] = (ops / kern_s) / max(meas, meas2)
+            meas, meas2 = nn.probe_fp32(0), nn.probe_fp32(1)
+            roof["peak_measured"] = max(meas, meas2) / 1e12
+            roof["peak_measured_scalar"] = meas / 1e12
+            roof["peak_measured_f32x2"] = meas2 / 1e12
+            roof["frac_of_measured"] = (3.0 * k * m * leg["n_local"] / (kern_ms_avg * 1e-3)) / max(meas, meas2)
         except Exception as e:  # measurement aid only
-            line_roof["peak_measured_error"] = str(e)
+            roof["peak_measured_error"] = str(e)
 
-    # ---- e2e: the C-ABI host entry with pinned host buffers, rank 0 drives all N GPUs -------------
-    e2e = None
-    if not args.no_e2e:
-        Rh_parts = [R.cpu()]
-        if world > 1:
-            gathered = [torch.empty_like(R) for _ in range(world)] if rank == 0 else None
-            dist.gather(R, gathered, dst=0)
-            if rank == 0:
-                Rh_parts = [g.cpu() for g in gathered]
-                del gathered
-            torch.cuda.synchronize()
-            dist.barrier(group=host_group)  # the other ranks now wait on the CPU, their GPUs are idle
+    # ---- e2e + oracle spot check (rank 0 holds the whole reference set on the host) -----------------
+    e2e, parity, parity_n = None, None, 0
+    need_host = not args.no_e2e
+    if need_host:
+        Rh = gather_references(leg["R"], world, rank, host_group)
         if rank == 0:
-            Sh = S.cpu().pin_memory()
-            Rh = torch.cat(Rh_parts).pin_memory()
-            res = np.empty(m, dtype=np.int32)
-            for _ in range(2):
-                nn.search_host(Sh, Rh, k, num_gpus=world, out=res)
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                nn.search_host(Sh, Rh, k, num_gpus=world, out=res)
-            t_e2e = (time.perf_counter() - t0) / args.steps
-            torch.cuda.synchronize()
-            same = bool(np.array_equal(res, out.cpu().numpy()))
-            e2e = {"value": pairs_per_step / t_e2e, "unit": UNIT, "ms_per_call": t_e2e * 1e3,
-                   "h2d_bytes_per_step": int((m * k + n_total * k) * 4), "d2h_bytes_per_step": int(m * 4),
-                   "api": "nn_b200_search_host (body of cudaCallback), pinned host buffers, "
-                          f"{world} GPU(s) driven from one process",
-                   "matches_device_resident_result": same}
-            # the same call against a RESIDENT reference index (build once, query many): only the
-            # queries and the indices cross PCIe
-            with nn.Index(Rh, k, num_gpus=world) as ix:
-                res2 = np.empty(m, dtype=np.int32)
-                for _ in range(2):
-                    ix.search(Sh, out=res2)
-                t0 = time.perf_counter()
-                for _ in range(args.steps):
-                    ix.search(Sh, out=res2)
-                t_ix = (time.perf_counter() - t0) / args.steps
-            e2e["resident_index"] = {"value": pairs_per_step / t_ix, "unit": UNIT, "ms_per_call": t_ix * 1e3,
-                                     "h2d_bytes_per_step": int(m * k * 4), "d2h_bytes_per_step": int(m * 4),
-                                     "api": "nn_b200_index_search (references resident in HBM)",
-                                     "matches": bool(np.array_equal(res2, res))}
-            del Rh, Sh
+            Sh = leg["S"].cpu().numpy()
+            calls = max(1, min(args.steps, 5 if pairs_per_step > 2e11 else 20))
+            e2e, results = e2e_leg(nn, k, m, n_total, Sh, Rh, calls, world)
+            results["device_resident" + ("_nccl_merge" if world > 1 else "")] = leg["out"].cpu().numpy()
+            parity, parity_n = spot_check(k, m, Sh, Rh, results)
+            e2e["matches_device_resident_result"] = bool(np.array_equal(results["cudaCallback"], leg["out"].cpu().numpy()))
         if world > 1:
             torch.cuda.synchronize()
             dist.barrier(group=host_group)
@@ -462,35 +591,84 @@ def main():
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        Sh, Rh = S.cpu().numpy(), R.cpu().numpy()
-        cpu = cpu_arm(k, m, n_local, Sh, Rh, budget_s=12.0)
+        Sh2 = leg["S"].cpu().numpy()
+        Rh2 = Rh if need_host else leg["R"].cpu().numpy()
+        cpu = cpu_arm(k, m, n_total, Sh2, Rh2, budget_s=12.0)
         cpu.pop("seconds", None)
-        # the same sample doubles as a parity spot-check of the measured result
-        from oracle import oracle
-        rows = np.arange(0, m, max(1, m // 16))[:16]
-        want = oracle.v0(Sh[rows], Rh, k, threads=0)
-        cpu["parity_spot_check"] = bool(np.array_equal(out.cpu().numpy()[rows], want))
+    main_S, main_out = leg["S"], leg["out"]
+    launches, plan, wall_s = leg["launches"], leg["plan"], leg["wall_s"]
+    del leg
+    if need_host and rank == 0:
+        del Rh
+    torch.cuda.empty_cache()
+
+    # ---- every other BASELINE config, short (N = 1) -----------------------------------------------
+    all_cfg = None
+    if rank == 0 and world == 1 and not args.no_all_configs:
+        all_cfg = {}
+        for name in sorted(WORKLOADS):
+            if name == args.workload:
+                continue
+            kk, mm, nn_ = WORKLOADS[name]
+            st = max(3, min(args.steps, 10 if mm * nn_ < 5e11 else 5))
+            lg = device_leg(nn, kk, mm, nn_, st, 3, dev, seed=3000)
+            km = sum(lg["kern_ms"]) / len(lg["kern_ms"])
+            rf = roofline_of(kk, mm, nn_, km, peaks, sms, lg["plan"], name)
+            entry = {"workload": DESCR[name], "k": kk, "m": mm, "n": nn_, "steps": st, "ms_per_step": km,
+                     "value": float(mm) * nn_ / (km * 1e-3), "unit": UNIT, "plan": lg["plan"],
+                     "gpu_launches_per_step": lg["launches"] / st,
+                     "roofline": {kx: rf[kx] for kx in ("bound", "kernel", "achieved", "peak", "unit", "frac", "kernel_ms",
+                                                        "traffic")},
+                     "step_ms_min_max": [min(lg["step_ms"]), max(lg["step_ms"])]}
+            if not args.no_e2e:
+                Sh, Rh = lg["S"].cpu().numpy(), lg["R"].cpu().numpy()
+                ee, res = e2e_leg(nn, kk, mm, nn_, Sh, Rh, 3, 1, full=False)
+                res["device_resident"] = lg["out"].cpu().numpy()
+                ok, nq = spot_check(kk, mm, Sh, Rh, res)
+                entry["e2e"] = {kx: ee[kx] for kx in ("value", "unit", "ms_per_call", "h2d_bytes_per_step",
+                                                      "d2h_bytes_per_step")}
+                entry["e2e"]["api"] = "cudaCallback, malloc'ed pageable host arrays"
+                entry["parity_spot_check"] = all(ok.values())
+                entry["parity_detail"] = {"oracle_queries": nq, **ok}
+                del Sh, Rh
+            all_cfg[name] = entry
+            del lg
+            torch.cuda.empty_cache()
+        # the reference's own GPU kernels, recompiled for this GPU, on the shapes where they are valid
+        torch.cuda.synchronize()
+        all_cfg["reference_gpu_on_this_b200"] = reference_gpu_leg()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": DESCR[args.workload] + (f"; {world} shards, n_total={n_total}" if world > 1 else ""),
-                       "k": k, "m": m, "n_per_gpu": n_local, "n_total": n_total,
-                       "parallelism": f"reference shards x{world}, NCCL all-reduce(min) of uint64 keys" if world > 1 else "1 GPU",
+            "config": {"workload": workload_string(args.workload, args.scaling, world),
+                       "k": k, "m": m, "n_total": n_total,
+                       "parallelism": (f"{world} reference shards of one set (strong scaling), one process per GPU, "
+                                       "NCCL all-reduce(min) of uint64 keys" if world > 1 and args.scaling == "strong"
+                                       else (f"reference shards x{world} (weak), NCCL all-reduce(min) of uint64 keys"
+                                             if world > 1 else "1 GPU")),
                        "l2": "flushed between steps (256 MiB written then 256 MiB read, outside the event window)",
                        "timing": "CUDA events per step on the launching stream, summed over the K steps, max over ranks; "
                                  "one untimed priming step between the synchronize and the first timed step",
-                       "plan": plan, "uniform [0,1) float32": True},
-            "roofline": line_roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+                       "step": "one launch: nn_b200_search_device (search + merge + index store)" if world == 1 else
+                               "search (one launch, final keys of the shard) -> all-reduce(min) -> keys_unpack",
+                       "plan": plan, "data": "uniform [0,1) float32, seeded"},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "parity_spot_check": (all(parity.values()) if parity else None),
+            "parity_detail": ({"oracle_queries": parity_n, "oracle": "oracle/nn_oracle.c v0 restatement, full reference set",
+                               **parity} if parity else None),
+            "all_configs": all_cfg,
+            "clocks": clocks, "wall_ms_per_step_incl_flush": 1e3 * wall_s / args.steps,
             "step_ms_min_max": [min(step_ms), max(step_ms)], "step_ms": [round(x, 4) for x in step_ms[:32]],
             "merge_ms": sum(merge_ms) / len(merge_ms),
-            "kernel_ms_min_max_over_ranks": [float(kern_lo.item()), float(kern_hi.item())],
+            "kernel_ms_min_max_over_ranks": [float(t_min[1].item()), float(t_max[1].item())],
+            "step_ms_per_rank": per_rank_steps,
         }
         emit(line)
     if world > 1:
+        dist.barrier(group=host_group)
         dist.destroy_process_group()
 
 

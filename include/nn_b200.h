@@ -99,6 +99,35 @@ NN_B200_API int nn_b200_nearest_keys_soa(int k, int m, int64_t n, const float *d
                              uint32_t index_base, uint64_t *d_keys, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * 2a. The same search in ONE launch.
+ *     v7's device section is transpose -> search kernel -> copy-out (core.cu:726-764); the building
+ *     blocks above make it keys_init -> search -> keys_unpack.  For small problems (BASELINE config 1
+ *     is 16 us of arithmetic) the launches themselves weigh, so the search kernels can also finish
+ *     the job: the last CTA of every query tile to fold its candidates (a ticket counter decides)
+ *     stores results[i] and puts keys and ticket back into the start state.  The state lives in a
+ *     caller-owned WORKSPACE that is initialised once and is left initialised by every call.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Bytes of a workspace for searches of up to m queries (ticket counters + m packed keys). */
+NN_B200_API size_t nn_b200_workspace_bytes(int m);
+/* Once after allocation (device memory, 16-byte aligned): tickets = 0, keys = NN_B200_KEY_INIT. */
+NN_B200_API int nn_b200_workspace_init(void *d_ws, int m, void *stream);
+/* The workspace's key array (pure pointer arithmetic): a reference set that arrives in pieces is
+ * folded into it with nn_b200_nearest_keys, then nn_b200_workspace_finish emits the answer. */
+NN_B200_API uint64_t *nn_b200_workspace_keys(void *d_ws);
+/* results[i] = index of the nearest of the n references for each of the m queries (what
+ * cudaCallbackKernel + the host reduce leave in `results`, core.cu:853-854, 765-787), and/or
+ * keys_out[i] = the final packed key (input of a multi-GPU merge); either may be NULL, not both.
+ * One kernel launch for every plan except the diagnostic plain kernel.  The workspace must be in its
+ * initialised state and is left in it.  d_R must be 16-byte aligned. */
+NN_B200_API int nn_b200_search_device(int k, int m, int64_t n, const float *d_S, const float *d_R,
+                                      uint32_t index_base, void *d_ws, int *d_results, uint64_t *d_keys_out,
+                                      void *stream);
+/* Emits results / keys_out from the workspace's keys and restores its initialised state (one small
+ * kernel): the closing step after folding several pieces with nn_b200_nearest_keys. */
+NN_B200_API int nn_b200_workspace_finish(void *d_ws, int m, int *d_results, uint64_t *d_keys_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * 2b. Resident reference index: build once, query many times.
  *     The reference pays the host->device copy of the reference set on every call
  *     (core.cu:885-891); its only build-once/query-many variants are the KD-trees v9/v10
@@ -131,6 +160,14 @@ NN_B200_API int nn_b200_shard_range(int64_t n, int num_shards, int shard, int64_
 /* Number of CUDA devices the host entry would use for n references (core.cu:865-868). */
 NN_B200_API int nn_b200_device_count(int64_t n);
 
+/* GPUs the host entry uses for a call when the caller names no count (pure arithmetic, no device
+ * needed): the analogue of the reference's device-count clamp and small-n single-GPU shortcut
+ * (core.cu:865-872).  Sharding divides the copy and the search but costs a host thread per GPU and the
+ * merge, so small calls stay on one GPU.  `visible` = GPUs available (nn_b200_device_count). */
+NN_B200_API int nn_b200_plan_gpus(int k, int m, int64_t n, int visible);
+/* GPUs the most recent nn_b200_cudaCallback / nn_b200_search_host call of this process used. */
+NN_B200_API int nn_b200_last_gpus(void);
+
 /* Loads every search kernel (all k, all tile shapes) on the current device so that no later call
  * pays the lazy code loading of a first use (about 1-3 ms per kernel).  The reference hides the same
  * cold start with its static WarmUP object (core.cu:1274).  The host entry points call it once per
@@ -144,8 +181,9 @@ NN_B200_API int64_t nn_b200_launch_count(void);
 NN_B200_API const char *nn_b200_last_error(void);
 
 /* Tuning knobs for benchmarking/sweeps; production code never needs them.  Known names:
- * "variant" (0 auto, 1 query-register kernel, 2 reference-register kernel, 3 plain kernel, 4 reference-stream kernel),
- * "splits" (0 auto), "h2d_chunk_bytes", "p2p_merge" (multi-GPU host entry: 1 = the search kernels of
+ * "variant" (0 auto, 1 query-register kernel, 2 reference-register kernel, 3 plain kernel, 4 reference-stream kernel,
+ * 5 phased query-register kernel),
+ * "splits" (0 auto), "h2d_chunk_bytes", "auto_gpus" (1: nn_b200_plan_gpus picks the GPU count of a host call, 0: all visible), "p2p_merge" (multi-GPU host entry: 1 = the search kernels of
  * every GPU fold into GPU 0's key array with system-scope atomics over NVLink, 0 = NCCL all-reduce).
  * Returns NN_B200_EINVAL for an unknown name. */
 NN_B200_API int nn_b200_set_option(const char *name, int64_t value);
@@ -161,9 +199,14 @@ NN_B200_API int nn_b200_probe_fp32(int mode, int iters, double *lane_ops_per_s);
 NN_B200_API int nn_b200_describe_plan(int k, int m, int64_t n, char *buf, size_t len);
 
 /* Which kernel family nn_b200_nearest_keys picks for m queries x n references of k dimensions (pure
- * arithmetic, no device needed): 1 query-register, 2 reference-register, 4 reference-stream;
+ * arithmetic, no device needed): 1 query-register, 2 reference-register, 4 reference-stream, 5 phased query-register;
  * NN_B200_EINVAL for a bad shape. */
 NN_B200_API int nn_b200_plan_variant(int k, int m, int64_t n);
+
+/* Layout of the phased query-register kernel for m queries (pure arithmetic): q queries per thread,
+ * `groups` x `phases` <= 128 threads per CTA, `qtiles` query tiles of `tile_queries` queries each
+ * (tile_queries <= groups * q, qtiles * tile_queries >= m). */
+NN_B200_API int nn_b200_plan_flex(int k, int m, int *q, int *groups, int *phases, int *qtiles, int *tile_queries);
 
 /* Introspection of the launch planner (pure arithmetic, no device needed): for the query-register
  * kernel with `q` queries per thread (tile = 128 q queries) at `occ` CTAs per SM on `sms` SMs, how

@@ -14,8 +14,8 @@ Host-side mirror of the reference's interface for this path:
 Everything computes in ``libnn_b200.so`` (hand-written sm_100a CUDA behind the C ABI of
 include/nn_b200.h).  There is no CPU fallback."""
 from ._lib import KEY_INIT, LIB_PATH, NNError, build, lib  # noqa: F401
-from .api import (Index, cudaCallback, describe_plan, device_count, launch_count, probe_fp32, search_host,  # noqa: F401
-                  set_option, shard_range)
+from .api import (Index, cudaCallback, describe_plan, device_count, last_gpus, launch_count, plan_gpus,  # noqa: F401
+                  probe_fp32, search_host, set_option, shard_range)
 
-__all__ = ["cudaCallback", "search_host", "Index", "describe_plan", "device_count", "launch_count", "set_option",
+__all__ = ["cudaCallback", "search_host", "Index", "describe_plan", "device_count", "launch_count", "plan_gpus", "last_gpus", "set_option",
            "shard_range", "probe_fp32", "KEY_INIT", "LIB_PATH", "NNError", "build", "lib"]

@@ -29,10 +29,20 @@ SIGNATURES = {
     "nn_b200_repack_soa": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nn_b200_nearest_keys_soa": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]),
+    "nn_b200_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "nn_b200_workspace_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "nn_b200_workspace_keys": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "nn_b200_search_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
+    "nn_b200_workspace_finish": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p]),
     "nn_b200_shard_range": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                            ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "nn_b200_device_count": (ctypes.c_int, [ctypes.c_int64]),
     "nn_b200_launch_count": (ctypes.c_int64, []),
+    "nn_b200_plan_gpus": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int]),
+    "nn_b200_last_gpus": (ctypes.c_int, []),
     "nn_b200_last_error": (ctypes.c_char_p, []),
     "nn_b200_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "nn_b200_probe_fp32": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
@@ -42,6 +52,7 @@ SIGNATURES = {
     "nn_b200_index_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int)]),
     "nn_b200_index_destroy": (None, [ctypes.c_void_p]),
     "nn_b200_warmup": (ctypes.c_int, []),
+    "nn_b200_plan_flex": (ctypes.c_int, [ctypes.c_int, ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 5),
     "nn_b200_plan_variant": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64]),
     "nn_b200_describe_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_char_p, ctypes.c_size_t]),
 }

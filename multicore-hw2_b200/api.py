@@ -47,24 +47,42 @@ def search_host(searchPoints, referencePoints, k: int | None = None, num_gpus: i
     R, r_ptr = _as_host(referencePoints)
     if k is None:
         k = int(S.shape[-1])
-    m = S.size // k if hasattr(S, "size") and not callable(S.size) else S.numel() // k
-    n = R.size // k if hasattr(R, "size") and not callable(R.size) else R.numel() // k
+    m, n = _count(S, k), _count(R, k)
     if out is None:
         out = np.empty(m, dtype=np.int32)
-    o, o_ptr = _as_host(out, dtype="int32")
+    o, o_ptr = _as_host(out, dtype="int32", output=True)
+    if _count(o, 1) < m:
+        raise ValueError("`out` is smaller than the number of queries")
     check(lib().nn_b200_search_host(k, m, n, s_ptr, r_ptr, o_ptr, num_gpus))
     return out
 
 
-def _as_host(a, dtype: str = "float32"):
-    """(object kept alive, raw pointer) for a numpy array or a torch CPU tensor."""
+def _as_host(a, dtype: str = "float32", output: bool = False):
+    """(object kept alive, raw pointer) for a numpy array or a torch CPU tensor of exactly `dtype`.
+    Inputs of another dtype or layout are converted (a copy); an OUTPUT buffer must already be a
+    contiguous array of the right dtype -- results written into a silent copy would be lost."""
     if hasattr(a, "data_ptr"):  # torch tensor
+        import torch
         if a.is_cuda:
             raise ValueError("host entry point takes host buffers; use multicore_hw2_b200.device for CUDA tensors")
-        a = a.contiguous()
+        want = getattr(torch, dtype)
+        if output:
+            if a.dtype != want or not a.is_contiguous():
+                raise ValueError(f"`out` must be a contiguous {dtype} tensor")
+        else:
+            a = a.to(want).contiguous()
         return a, a.data_ptr()
+    if output:
+        if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags["C_CONTIGUOUS"] \
+                or not a.flags["WRITEABLE"]:
+            raise ValueError(f"`out` must be a writeable C-contiguous numpy array of dtype {dtype}")
+        return a, a.ctypes.data
     a = np.ascontiguousarray(a, dtype=dtype)
     return a, a.ctypes.data
+
+
+def _count(a, k: int) -> int:
+    return (a.numel() if hasattr(a, "numel") else a.size) // k
 
 
 def shard_range(n: int, num_shards: int, shard: int):
@@ -80,6 +98,15 @@ def device_count(n: int = 1 << 30) -> int:
 
 def launch_count() -> int:
     return lib().nn_b200_launch_count()
+
+
+def plan_gpus(k: int, m: int, n: int, visible: int) -> int:
+    """GPUs a host-entry call would use out of `visible` (pure arithmetic; core.cu:865-872's job)."""
+    return lib().nn_b200_plan_gpus(k, m, n, visible)
+
+
+def last_gpus() -> int:
+    return lib().nn_b200_last_gpus()
 
 
 def set_option(name: str, value: int) -> None:
@@ -109,7 +136,7 @@ class Index:
         R, r_ptr = _as_host(referencePoints)
         if k is None:
             k = int(R.shape[-1])
-        n = R.size // k if hasattr(R, "size") and not callable(R.size) else R.numel() // k
+        n = _count(R, k)
         self._h = ctypes.c_void_p()
         check(lib().nn_b200_index_create(k, n, r_ptr, num_gpus, ctypes.byref(self._h)))
         self.k, self.n = k, n
@@ -121,10 +148,12 @@ class Index:
         if not self._h:
             raise ValueError("index is closed")
         S, s_ptr = _as_host(searchPoints)
-        m = S.size // self.k if hasattr(S, "size") and not callable(S.size) else S.numel() // self.k
+        m = _count(S, self.k)
         if out is None:
             out = np.empty(m, dtype=np.int32)
-        o, o_ptr = _as_host(out, dtype="int32")
+        o, o_ptr = _as_host(out, dtype="int32", output=True)
+        if _count(o, 1) < m:
+            raise ValueError("`out` is smaller than the number of queries")
         check(lib().nn_b200_index_search(self._h, m, s_ptr, o_ptr))
         return out
 

@@ -66,7 +66,7 @@ struct Cfg
     int k = 16, m = 4096;
     long long n = 1 << 20;
     int variant = 0, q = 0, scalar = 2, splits = 0, waves = 4, iters = 10, warmup = 3, check = 0, soa = 0, repack = 0,
-        rreg_ctas = 0, quant = 0, ldg = 0;
+        rreg_ctas = 0, quant = 0, ldg = 0, fused = 0;
     std::string tag;
 };
 
@@ -140,8 +140,29 @@ static void run(const Cfg &c)
     if (!c.soa)
         NN(nn_b200_describe_plan(c.k, c.m, c.n, plan, sizeof plan));
 
+    // --fused 1: the one-launch search (workspace + nn_b200_search_device): no init, no unpack
+    void *dWs = nullptr;
+    int *dOut = nullptr;
+    if (c.fused)
+    {
+        CK(cudaMalloc(&dWs, nn_b200_workspace_bytes(c.m)));
+        CK(cudaMalloc(&dOut, std::max(c.m, 1) * sizeof(int)));
+        NN(nn_b200_workspace_init(dWs, c.m, nullptr));
+    }
     for (int it = 0; it < c.warmup + c.iters; ++it)
     {
+        if (c.fused)
+        {
+            CK(cudaEventRecord(e0));
+            NN(nn_b200_search_device(c.k, c.m, c.n, dS, dR, 0, dWs, dOut, c.fused == 2 ? dK : nullptr, nullptr));
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float t;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            if (it >= c.warmup)
+                ms.push_back(t);
+            continue;
+        }
         NN(nn_b200_keys_init(dK, c.m, nullptr));
         CK(cudaEventRecord(e0));
         if (c.soa)
@@ -173,6 +194,27 @@ static void run(const Cfg &c)
         CK(cudaMemcpy(a.data(), dK, (size_t)c.m * 8, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(b.data(), dK2, (size_t)c.m * 8, cudaMemcpyDeviceToHost));
         mismatches = 0;
+        if (c.fused)
+        { // indices of the one-launch search against the plain kernel's; fused == 2 also returned the keys
+            std::vector<int> r(c.m);
+            CK(cudaMemcpy(r.data(), dOut, (size_t)c.m * sizeof(int), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < c.m; ++i)
+            {
+                if ((uint32_t)r[i] != (uint32_t)(b[i] & 0xffffffffu))
+                    ++mismatches;
+                if (c.fused != 2)
+                    a[i] = b[i];
+            }
+            // the workspace must be back in its start state: a second search gives the same answer
+            NN(nn_b200_set_option("variant", c.variant));
+            NN(nn_b200_search_device(c.k, c.m, c.n, dS, dR, 0, dWs, dOut, nullptr, nullptr));
+            CK(cudaDeviceSynchronize());
+            std::vector<int> r2(c.m);
+            CK(cudaMemcpy(r2.data(), dOut, (size_t)c.m * sizeof(int), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < c.m; ++i)
+                if (r2[i] != r[i])
+                    ++mismatches;
+        }
         for (int i = 0; i < c.m; ++i)
             if (a[i] != b[i])
             {
@@ -184,14 +226,19 @@ static void run(const Cfg &c)
         NN(nn_b200_set_option("variant", c.variant));
     }
 
-    printf("{\"op\":\"nearest_keys\",\"tag\":\"%s\",\"k\":%d,\"m\":%d,\"n\":%lld,\"soa\":%d,\"quant\":%d,\"ms_med\":%.4f,"
+    printf("{\"op\":\"%s\",\"tag\":\"%s\",\"k\":%d,\"m\":%d,\"n\":%lld,\"soa\":%d,\"quant\":%d,\"ms_med\":%.4f,"
            "\"ms_best\":%.4f,\"pairs_per_s\":%.4e,\"fp32_frac_maxclk\":%.4f,\"GBps\":%.1f,\"mismatch_vs_plain\":%lld,"
            "\"plan\":\"%s\"}\n",
-           c.tag.c_str(), c.k, c.m, c.n, c.soa, c.quant, med, best, pairs / (med * 1e-3), ops / (med * 1e-3) / g_peak_ops,
+           c.fused ? "search_device" : "nearest_keys", c.tag.c_str(), c.k, c.m, c.n, c.soa, c.quant, med, best,
+           pairs / (med * 1e-3), ops / (med * 1e-3) / g_peak_ops,
            bytes / med / 1e6, mismatches, plan);
     fflush(stdout);
     if (dRs)
         CK(cudaFree(dRs));
+    if (dWs)
+        CK(cudaFree(dWs));
+    if (dOut)
+        CK(cudaFree(dOut));
     CK(cudaFree(dS));
     CK(cudaFree(dR));
     CK(cudaFree(dK));
@@ -238,6 +285,10 @@ int main(int argc, char **argv)
             c.ldg = atoi(val());
         else if (a == "--quant")
             c.quant = atoi(val());
+        else if (a == "--fused")
+            c.fused = atoi(val());
+        else if (a == "--tag")
+            c.tag = val();
         else if (a == "--sweep")
             sweep = val();
         else
@@ -285,7 +336,8 @@ int main(int argc, char **argv)
     }
     if (sweep.empty())
     {
-        c.tag = "single";
+        if (c.tag.empty())
+            c.tag = "single";
         run(c);
         return 0;
     }
@@ -351,6 +403,22 @@ int main(int argc, char **argv)
             add("repack", k, 1, 1 << 26, 0, 0, 2, 4, 0, 0, 1);
         add("repack", 16, 1, (1 << 24) + 3, 0, 0, 2, 4, 0, 0, 1);
     }
+    else if (sweep == "cross")
+    {
+        // kernel-family crossover over the few-query band: every family on every shape, plus the
+        // planner's own pick (tag "auto"); scripts/make_crossover.py turns the lines into
+        // profiles/r02_fewquery_crossover.json, which the CPU test of nn_b200_plan_variant reads
+        for (int k : {3, 8, 16})
+            for (long long n : {1LL << 16, 1LL << 20, 1LL << 22})
+                for (int m : {5, 8, 9, 16, 24, 25, 32, 48, 64, 100, 112, 128, 200, 256, 500})
+                {
+                    add("auto", k, m, n, 0, 0, 2, 8, 0);
+                    add("qreg", k, m, n, 1, 0, 2, 8, 0);
+                    if (m <= 64)
+                        add("rtma", k, m, n, 4, 0, 2, 8, 0);
+                    add("qflex", k, m, n, 5, 0, 2, 8, 0);
+                }
+    }
     else if (sweep == "check")
     {
         // correctness against the plain kernel on tie-heavy data, all k, awkward sizes
@@ -375,6 +443,10 @@ int main(int argc, char **argv)
             x.variant = 4;
             x.m = 15;
             list.push_back(x);
+            x.variant = 5;
+            x.m = 100 + k;
+            list.push_back(x);
+            x.m = 15;
             x.variant = 2;
             x.soa = 1;
             list.push_back(x);

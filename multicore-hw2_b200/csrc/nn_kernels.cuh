@@ -84,6 +84,7 @@ namespace nnb200
 constexpr int kQregUnroll = NN_QREG_UNROLL;
 constexpr unsigned long long KEY_INIT = 0x7F80000000000000ull;
 constexpr uint32_t NO_REF = 0xFFFFFFFFu;
+constexpr unsigned long long KEY_NONE = 0xFFFFFFFFFFFFFFFFull; // "no candidate": larger than every real key
 
 __device__ __forceinline__ unsigned long long pack_key(float d2, uint32_t idx)
 {
@@ -100,6 +101,58 @@ __device__ __forceinline__ void fold_key(unsigned long long *slot, unsigned long
         atomicMin_system(slot, key);
     else
         atomicMin(slot, key);
+}
+
+// Last-CTA-finishes protocol (struct Finish, nn_launch.h).  Called by every thread of the CTA after
+// its folds.  The CTAs of a ticket group count themselves on tickets[group]; the one that draws the
+// last ticket knows that every other CTA's folds are visible (each fenced before drawing), reads the
+// group's final keys at the L2, emits results / keys_out and restores the start state of keys and
+// ticket, so the workspace is ready for the next launch without an init kernel.
+// BAR_ID / BAR_THREADS: the CTA barrier the protocol synchronises on -- barrier 0 with all threads
+// (__syncthreads) or a named barrier over the first BAR_THREADS threads (kernels whose producer warp has
+// already left).  Ordering: every thread's folds happen-before the barrier; thread 0 then draws the
+// ticket with an acq_rel atomic at GPU scope (release: cumulative over what it observed through the
+// barrier; acquire: the last drawer sees every earlier CTA's folds), which is the CUTLASS semaphore
+// pattern and costs ONE fence per CTA instead of one per thread.
+template <int BAR_ID, int BAR_THREADS>
+__device__ __forceinline__ void cta_bar()
+{
+    if constexpr (BAR_ID == 0)
+        __syncthreads();
+    else
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_ID), "n"(BAR_THREADS) : "memory");
+}
+
+template <int BAR_ID = 0, int BAR_THREADS = 0>
+__device__ __forceinline__ void finish_group(const Finish &f, unsigned long long *keys, uint32_t group,
+                                             uint32_t expected, int q_begin, int q_count)
+{
+    if (f.tickets == nullptr) // (uniform over the grid)
+        return;
+    __shared__ uint32_t s_last;
+    const int nthr = BAR_ID == 0 ? (int)blockDim.x : BAR_THREADS;
+    cta_bar<BAR_ID, BAR_THREADS>();
+    if (threadIdx.x == 0)
+    {
+        uint32_t t;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(f.tickets + group) : "memory");
+        s_last = (t == expected - 1u) ? 1u : 0u;
+    }
+    cta_bar<BAR_ID, BAR_THREADS>();
+    if (s_last)
+    {
+        for (int i = threadIdx.x; i < q_count; i += nthr)
+        {
+            const unsigned long long key = __ldcg(keys + q_begin + i);
+            if (f.results)
+                f.results[q_begin + i] = (int)(unsigned int)(key & 0xffffffffull);
+            if (f.keys_out)
+                f.keys_out[q_begin + i] = key;
+            __stcg(keys + q_begin + i, KEY_INIT);
+        }
+        if (threadIdx.x == 0)
+            f.tickets[group] = 0u;
+    }
 }
 
 // References come in 16-byte-aligned groups of G points (G*K floats = F4 float4) so that every
@@ -419,8 +472,12 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
     const uint32_t r1 = (split == a.splits - 1) ? a.n : min(r0 + a.refs_per_split, a.n);
     const uint32_t r1c = r0 + ((r1 - r0) / CH) * CH;
     const uint32_t ntiles = (r1c - r0 + TR - 1) / TR;
+    const int qt_begin = (int)(qtile * (NT * Q));
     if (r1 <= r0)
+    { // (never planned: every split receives references) -- still counted by the finish protocol
+        finish_group(a.fin, a.keys, qtile, a.splits, qt_begin, min(NT * Q, a.m - qt_begin));
         return;
+    }
 
     auto issue = [&](uint32_t t, uint32_t stage) { // tile t of this CTA -> ring stage
         const uint32_t first = r0 + t * TR;
@@ -549,7 +606,12 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
             }
     }
 
-    // resolve the exact (lowest) index inside the winning chunk, then fold into the global keys
+    // resolve the exact (lowest) index inside the winning chunk, then fold into the global keys.
+    // A CTA whose whole range went through the ring without re-using a stage (small problems: BASELINE
+    // config 1 is 448 references per CTA) still holds every chunk in shared memory and re-reads the
+    // winner there; otherwise it comes from global memory (L2), whose latency -- two dependent round
+    // trips at Q = 2 -- was 12% of the warps' time at config 1 (ncu source view, r01_cfg1_qreg).
+    const bool in_ring = ntiles <= (uint32_t)STAGES && r1c == r1;
 #pragma unroll
     for (int j = 0; j < Q; ++j)
     {
@@ -557,7 +619,33 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
         if (bref[j] != NO_REF && qi < a.m)
         {
             uint32_t idx = bref[j];
-            if (VEC && bref[j] + CH <= a.n)
+            if (in_ring)
+            {
+                constexpr int G = Geo<K>::G, F4 = Geo<K>::F4;
+                const float4 *p4 = reinterpret_cast<const float4 *>(tiles + (size_t)(bref[j] - r0) * K);
+#pragma unroll
+                for (int g0 = CH - G; g0 >= 0; g0 -= G)
+                {
+                    float grp[G * K];
+#pragma unroll
+                    for (int i = 0; i < F4; ++i)
+                    {
+                        const float4 v = p4[(g0 / G) * F4 + i];
+                        grp[4 * i + 0] = v.x;
+                        grp[4 * i + 1] = v.y;
+                        grp[4 * i + 2] = v.z;
+                        grp[4 * i + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int g = G - 1; g >= 0; --g)
+                    {
+                        const float d = sqdist<K, 0, false>(q[j], &grp[g * K]);
+                        if (d == best[j])
+                            idx = bref[j] + g0 + g;
+                    }
+                }
+            }
+            else if (VEC && bref[j] + CH <= a.n)
             {
                 // whole chunk inside the set: it starts on a 16-byte boundary (chunk starts are
                 // multiples of 4 points), so it is re-read group by group with 128-bit loads -- a
@@ -603,6 +691,277 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
             fold_key(a.keys + qi, pack_key(best[j], a.index_base + idx), a.peer_keys);
         }
     }
+    finish_group(a.fin, a.keys, qtile, a.splits, qt_begin, min(NT * Q, a.m - qt_begin));
+}
+
+// =============================================================================================
+// Kernel A' -- "phased query-register" kernel, for query counts that do not fill 128-query tiles
+// (9 .. a few hundred queries).
+//
+// Kernel A gives every thread Q queries and lets all 128 threads walk the SAME references, so a
+// search of 100 queries either computes on a padded 128-query tile (and, at one query per thread,
+// without the pair-packed math) or -- in the reference-stream kernel C -- re-streams the reference
+// set once per 8 queries.  Here the 128 threads of a CTA are laid out as NG query groups x NP
+// PHASES (NG * NP <= 128, both chosen by the host for the query count): thread (g, p) keeps the Q
+// queries of group g in registers, exactly as in kernel A, but only visits the reference groups
+// p, p + NP, p + 2 NP, ... of each tile.  100 queries are then 25 groups of 4 queries x 5 phases = 125
+// busy lanes of 128 with the all-packed math of kernel A and ONE pass over the reference set.
+// Same TMA ring, same chunk-minimum / late index resolution as kernel A; a thread's chunk is CH/G
+// groups NP groups apart (consecutive phases read consecutive 16-byte-aligned groups, which keeps
+// the lanes of a warp that belong to different phases out of each other's shared-memory banks).
+// The phases of a query meet in shared memory at the end (the ring is reused as a [Q][128] key
+// array), so a CTA still issues one atomicMin per query.
+// =============================================================================================
+template <int K, int Q>
+__device__ __forceinline__ void qflex_chunk(const float *__restrict__ sm, const uint32_t gstride,
+                                            const float (&q)[Q][K], float (&cm)[Q], const float2 nz,
+                                            float4 (&nxt)[Geo<K>::F4], const bool more)
+{
+    constexpr int G = Geo<K>::G, F4 = Geo<K>::F4, CHG = QregCfg<K>::CH / Geo<K>::G;
+    static_assert(Q % 2 == 0, "pair-packed math needs an even number of queries per thread");
+    float hold[Q];
+#pragma unroll
+    for (int u = 0; u < CHG; ++u)
+    {
+        float grp[G * K];
+#pragma unroll
+        for (int i = 0; i < F4; ++i)
+        {
+            grp[4 * i + 0] = nxt[i].x;
+            grp[4 * i + 1] = nxt[i].y;
+            grp[4 * i + 2] = nxt[i].z;
+            grp[4 * i + 3] = nxt[i].w;
+        }
+        // the thread's next group is loaded while this one is computed; `more` is false only for the
+        // last chunk of a tile, whose successor would lie past the tile
+        if (u + 1 < CHG || more)
+        {
+            const float4 *n4 = reinterpret_cast<const float4 *>(sm + (size_t)(u + 1) * gstride);
+#pragma unroll
+            for (int i = 0; i < F4; ++i)
+                nxt[i] = n4[i];
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+        {
+            const int c = u * G + g;
+            float dist[Q];
+#pragma unroll
+            for (int j = 0; j < Q; j += 2)
+            {
+                float2 qp[K];
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+                    qp[i] = make_float2(q[j][i], q[j + 1][i]);
+                const float2 d2 = sqdist_pair<K>(qp, &grp[g * K], nz);
+                dist[j] = d2.x;
+                dist[j + 1] = d2.y;
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j)
+            {
+                if ((c & 1) == 0)
+                    hold[j] = dist[j];
+                else if (c == 1)
+                    cm[j] = fminf(hold[j], dist[j]);
+                else
+                    cm[j] = fminf(fminf(cm[j], hold[j]), dist[j]);
+            }
+        }
+    }
+}
+
+template <int K, int Q, int NT>
+__global__ void __launch_bounds__(NT, qreg_minb<K, Q, 2>()) nn_qflex_kernel(const QflexArgs a)
+{
+    using C = QregCfg<K>;
+    constexpr int G = Geo<K>::G, F4 = Geo<K>::F4, CH = C::CH, CHG = CH / G, STAGES = C::STAGES;
+    constexpr int UNR = Q >= 8 ? 1 : (Q >= 4 ? 2 : 4);
+    static_assert(CH % 2 == 0 && CH % G == 0, "chunks are whole groups and an even number of points");
+    static_assert((size_t)NT * Q * 8 <= (size_t)STAGES * C::TILE_BYTES, "the phase exchange reuses the ring");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tiles = reinterpret_cast<float *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);
+
+    const int tid = threadIdx.x;
+    const uint32_t split = blockIdx.x % a.splits;
+    const uint32_t qtile = blockIdx.x / a.splits;
+    const uint32_t ng = a.ng, np = a.np;
+    // lanes beyond NG*NP shadow the last phase of group 0 (same addresses: broadcast) and publish nothing
+    const bool live = (uint32_t)tid < ng * np;
+    const uint32_t g = live ? (uint32_t)tid % ng : 0u;
+    const uint32_t p = live ? (uint32_t)tid / ng : np - 1u;
+    const uint32_t round = np * CH;                  // references one step of all phases covers
+    const uint32_t gstride = np * (uint32_t)(G * K); // floats between two groups of one thread
+    const uint32_t tile_refs = a.tile_groups * G;    // per ring stage; a whole number of rounds
+
+    const uint32_t r0 = min(split * a.refs_per_split, a.n);
+    const uint32_t r1 = (split == a.splits - 1) ? a.n : min(r0 + a.refs_per_split, a.n);
+    const uint32_t r1c = r0 + ((r1 - r0) / round) * round; // whole rounds stream through the ring
+    const uint32_t ntiles = (r1c - r0 + tile_refs - 1) / tile_refs;
+    const int qt_begin = (int)(qtile * a.tile_queries);
+    const int qt_count = min((int)a.tile_queries, a.m - qt_begin);
+    if (r1 <= r0)
+    {
+        finish_group(a.fin, a.keys, qtile, a.splits, qt_begin, qt_count);
+        return;
+    }
+
+    auto issue = [&](uint32_t t, uint32_t stage) {
+        const uint32_t first = r0 + t * tile_refs;
+        const uint32_t bytes = min(tile_refs, r1c - first) * (uint32_t)(K * 4);
+        mbar_expect_tx(&full[stage], bytes);
+        bulk_g2s(tiles + (size_t)stage * C::TILE_FLOATS, a.R + (size_t)first * K, bytes, &full[stage]);
+    };
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            mbar_init(&full[s], 1);
+        mbar_fence_init();
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s)
+            if ((uint32_t)s < ntiles)
+                issue(s, s);
+    }
+
+    // this thread's queries: local query j*NG + g of the tile (clamped; surplus slots publish nothing)
+    float q[Q][K];
+    float best[Q];
+    uint32_t bref[Q];
+    const float2 nz = make_float2(a.neg_zero, a.neg_zero);
+#pragma unroll
+    for (int j = 0; j < Q; ++j)
+    {
+        const int lq = min(j * (int)ng + (int)g, qt_count - 1);
+        const float *src = a.S + (size_t)(qt_begin + lq) * K;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+            q[j][i] = __ldg(src + i);
+        best[j] = __int_as_float(0x7f800000);
+        bref[j] = NO_REF;
+    }
+    __syncthreads();
+
+    uint32_t stage = 0, parity = 0;
+    for (uint32_t t = 0; t < ntiles; ++t)
+    {
+        __syncthreads(); // everyone is done with tile t-1: its stage may be refilled
+        if (tid == 0 && t + STAGES - 1 < ntiles)
+            issue(t + STAGES - 1, (stage + STAGES - 1) % STAGES);
+        mbar_wait(&full[stage], parity);
+        const uint32_t ref0 = r0 + t * tile_refs;
+        const uint32_t nch = min(tile_refs, r1c - ref0) / round; // chunks per thread in this tile
+        const float *sm = tiles + (size_t)stage * C::TILE_FLOATS + (size_t)p * (G * K);
+        float4 nxt[F4];
+#pragma unroll
+        for (int i = 0; i < F4; ++i)
+            nxt[i] = reinterpret_cast<const float4 *>(sm)[i];
+#pragma unroll UNR
+        for (uint32_t c = 0; c < nch; ++c)
+        {
+            float cm[Q];
+            qflex_chunk<K, Q>(sm + (size_t)c * CHG * gstride, gstride, q, cm, nz, nxt, c + 1 < nch);
+#pragma unroll
+            for (int j = 0; j < Q; ++j)
+                if (cm[j] < best[j])
+                {
+                    best[j] = cm[j];
+                    bref[j] = ref0 + (p + np * c * CHG) * G;
+                }
+        }
+        if (++stage == STAGES)
+        {
+            stage = 0;
+            parity ^= 1;
+        }
+    }
+
+    if (r1c < r1)
+    {
+        // ragged end of the range (less than one round): plain loads, padded with NaN up to a whole
+        // round (a NaN distance never wins)
+        __syncthreads();
+        const float *src = a.R + (size_t)r1c * K;
+        const uint32_t have = (r1 - r1c) * K;
+        for (uint32_t i = tid; i < round * K; i += NT)
+            tiles[i] = (i < have) ? __ldg(src + i) : __int_as_float(0x7fffffff);
+        __syncthreads();
+        const float *sm = tiles + (size_t)p * (G * K);
+        float4 nxt[F4];
+#pragma unroll
+        for (int i = 0; i < F4; ++i)
+            nxt[i] = reinterpret_cast<const float4 *>(sm)[i];
+        float cm[Q];
+        qflex_chunk<K, Q>(sm, gstride, q, cm, nz, nxt, false);
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+            if (cm[j] < best[j])
+            {
+                best[j] = cm[j];
+                bref[j] = r1c + p * G;
+            }
+    }
+
+    // The phases of every query meet in shared memory (the ring becomes best[Q][NT], chunk[Q][NT]).
+    // One thread per query then takes the minimum over the phases and resolves the exact (lowest)
+    // index ONLY in the winning chunk(s): groups chunk + u*NP*G, points g, re-read from global memory
+    // with v0's arithmetic.  (Every thread resolving its own Q candidates first cost Q dependent L2
+    // round trips per thread -- 8 at Q = 8 -- for candidates of which all but one per query lose.)
+    __syncthreads();
+    float *xb = reinterpret_cast<float *>(smem_raw);
+    uint32_t *xr = reinterpret_cast<uint32_t *>(xb + Q * NT);
+#pragma unroll
+    for (int j = 0; j < Q; ++j)
+    {
+        xb[j * NT + tid] = best[j];
+        xr[j * NT + tid] = live ? bref[j] : NO_REF;
+    }
+    __syncthreads();
+    for (uint32_t s = tid; s < ng * Q; s += NT)
+    {
+        if ((int)s >= qt_count) // local query s = j*NG + gg
+            continue;
+        const uint32_t j = s / ng, gg = s % ng;
+        float bmin = __int_as_float(0x7f800000);
+        bool any = false;
+        for (uint32_t pp = 0; pp < np; ++pp)
+            if (xr[j * NT + pp * ng + gg] != NO_REF)
+            {
+                bmin = fminf(bmin, xb[j * NT + pp * ng + gg]);
+                any = true;
+            }
+        if (!any)
+            continue; // nothing beat v0's start state in this CTA's range
+        float qv[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+            qv[i] = __ldg(a.S + (size_t)(qt_begin + (int)s) * K + i);
+        uint32_t idx = NO_REF;
+        for (uint32_t pp = 0; pp < np; ++pp)
+        {
+            const uint32_t c0 = xr[j * NT + pp * ng + gg];
+            if (c0 == NO_REF || xb[j * NT + pp * ng + gg] != bmin)
+                continue;
+#pragma unroll
+            for (int u = 0; u < CHG; ++u)
+            {
+#pragma unroll
+                for (int pt = 0; pt < G; ++pt)
+                {
+                    const uint32_t r = c0 + (uint32_t)u * np * G + pt;
+                    if (r < a.n)
+                    {
+                        const float d = sqdist_gmem<K>(qv, a.R + (size_t)r * K);
+                        if (d == bmin)
+                            idx = min(idx, r);
+                    }
+                }
+            }
+        }
+        fold_key(a.keys + qt_begin + (int)s, pack_key(bmin, a.index_base + idx), a.peer_keys);
+    }
+    finish_group(a.fin, a.keys, qtile, a.splits, qt_begin, qt_count);
 }
 
 // =============================================================================================
@@ -638,6 +997,7 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
     constexpr int P = G * PS;     // references per thread per slot
     constexpr int NP = MQ / 2;    // query pairs
     __shared__ __align__(16) float2 sq[NP * K]; // sq[pair*K + d] = (qa_d, qb_d)
+    __shared__ unsigned long long wkeys[NT / 32][MQ]; // per-warp results, merged per CTA at the end
 
     const int tid = threadIdx.x;
     const int pass = blockIdx.y;
@@ -852,9 +1212,20 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
             key = other < key ? other : key;
         }
-        if (lane == 0 && j < valid_q && key < (KEY_INIT | NO_REF))
-            fold_key(a.keys + q0 + j, key, a.peer_keys);
+        if (lane == 0)
+            wkeys[tid >> 5][j] = key;
     }
+    __syncthreads(); // one atomicMin per CTA and query (see nn_rtma_kernel)
+    if (tid < MQ && tid < valid_q)
+    {
+        unsigned long long kmin = wkeys[0][tid];
+#pragma unroll
+        for (int w = 1; w < NT / 32; ++w)
+            kmin = wkeys[w][tid] < kmin ? wkeys[w][tid] : kmin;
+        if (kmin < (KEY_INIT | NO_REF))
+            fold_key(a.keys + q0 + tid, kmin, a.peer_keys);
+    }
+    finish_group(a.fin, a.keys, (uint32_t)pass, gridDim.x, q0, valid_q);
 }
 
 // =============================================================================================
@@ -987,11 +1358,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);
     uint64_t *empty = full + STAGES;
     float2 *sq = reinterpret_cast<float2 *>(empty + STAGES); // sq[pair*K + d] = (qa_d, qb_d)
+    __shared__ unsigned long long wkeys[NW][MQ];             // per-warp results, merged per CTA at the end
 
     const int tid = threadIdx.x;
     const int pass = blockIdx.y;
     const int q0 = pass * MQ;
     const int valid_q = min(MQ, a.mq_total - q0); // >= 1
+    for (int i = tid; i < NW * MQ; i += (NW + 1) * 32)
+        (&wkeys[0][0])[i] = KEY_NONE;
     for (int i = tid; i < NP * K; i += (NW + 1) * 32)
     {
         const int pr = i / K, d = i % K;
@@ -1034,7 +1408,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
                 }
             }
         }
-        return;
+        return; // (the consumers' closing barriers are named barriers over their NTC threads)
     }
 
     // ---- consumer warps ----
@@ -1282,6 +1656,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
     // p from the lanes' registers with shuffles and evaluates it with v0's arithmetic.
     constexpr int F = P * K;             // floats of one thread's references in a tile
     constexpr int NV = (F + 31) / 32;    // registers per lane holding them
+    static_assert(NV <= 2 && P <= 32, "index resolution shuffles v[0], v[1] only and lets lane p evaluate reference p: "
+                                      "keep NN_RTMA_SLOT_FLOATS <= 64 and at most 32 references per thread and tile");
     const int warp_tid0 = tid - lane;    // first consumer thread of this warp
     auto load_cand = [&](uint32_t tile, int src, float(&v)[NV]) {
 #pragma unroll
@@ -1344,7 +1720,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
     for (int j = 0; j < MQ; ++j)
     {
         if (!masks[j])
-            continue; // nothing beat the start state for this query in this warp
+            continue; // nothing beat the start state for this query in this warp (its slot stays KEY_NONE)
         uint32_t idx = eval_cand(j, tiles[j], __ffs(masks[j]) - 1, vals[j], wmins[j]);
         for (uint32_t rest = masks[j] & (masks[j] - 1); rest; rest &= rest - 1)
         { // further lanes tied at the warp minimum (rare): same procedure, one after the other
@@ -1354,9 +1730,23 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
             load_cand(tile, src, v);
             idx = min(idx, eval_cand(j, tile, src, v, wmins[j]));
         }
-        if (lane == 0 && j < valid_q)
-            fold_key(a.keys + q0 + j, pack_key(wmins[j], a.index_base + idx), a.peer_keys);
+        if (lane == 0)
+            wkeys[tid >> 5][j] = pack_key(wmins[j], a.index_base + idx);
     }
+    // One atomicMin per CTA and query: the warps' keys meet in shared memory first.  (Every warp of
+    // every CTA folding on its own meant 148 x 12 atomics on each of the pass's 8 addresses, all at the
+    // end of the kernel and serialised at one L2 slice: 20.5 -> 14.0 us for a one-tile-per-CTA launch.)
+    cta_bar<1, NTC>();
+    if (tid < MQ && tid < valid_q)
+    {
+        unsigned long long kmin = wkeys[0][tid];
+#pragma unroll
+        for (int w = 1; w < NW; ++w)
+            kmin = wkeys[w][tid] < kmin ? wkeys[w][tid] : kmin;
+        if (kmin != KEY_NONE)
+            fold_key(a.keys + q0 + tid, kmin, a.peer_keys);
+    }
+    finish_group<1, NTC>(a.fin, a.keys, (uint32_t)pass, gridDim.x, q0, valid_q);
 }
 
 // =============================================================================================

@@ -3,6 +3,7 @@
 // and every inner loop over the dimensions is fully unrolled.
 #include "nn_kernels.cuh"
 
+#include <atomic>
 #include <type_traits>
 
 #ifndef NN_K
@@ -12,18 +13,38 @@
 namespace nnb200
 {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, so the
+// "already opted in" flag of a kernel is one bit per device ordinal.
+struct PerDeviceOnce
+{
+    std::atomic<uint64_t> done{0};
+    template <class F>
+    cudaError_t operator()(F set)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess)
+            return e;
+        const uint64_t bit = 1ull << (dev & 63);
+        if (done.load(std::memory_order_acquire) & bit)
+            return cudaSuccess;
+        e = set();
+        if (e == cudaSuccess)
+            done.fetch_or(bit, std::memory_order_release);
+        return e;
+    }
+};
+
 template <int K, int Q, int NT, int MATH>
 static cudaError_t launch_qreg_one(const QregArgs &a, uint32_t qtiles, cudaStream_t st)
 {
     auto kern = nn_qreg_kernel<K, Q, NT, MATH>;
-    static bool configured = false;
-    if (!configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QregCfg<K>::SMEM);
-        if (e != cudaSuccess)
-            return e;
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    const cudaError_t e = once([&] {
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QregCfg<K>::SMEM);
+    });
+    if (e != cudaSuccess)
+        return e;
     kern<<<qtiles * a.splits, NT, QregCfg<K>::SMEM, st>>>(a);
     return cudaGetLastError();
 }
@@ -53,8 +74,8 @@ static cudaError_t query_qreg_one(LaunchInfo *info, int *tile_queries, int *tile
 
 // q_sel: 0 = wide default tile, otherwise the requested queries/thread (1, 2, 4, 8; only tiles up
 // to the default width are built for a given k -- wider ones would spill).
-// math: 2 = f32x2 over query pairs (default; needs Q >= 2, Q = 1 falls back to mode 1),
-//       1 = f32x2 over dimension pairs, 0 = scalar (both kept for A/B measurements).
+// math: 2 = f32x2 over query pairs (default; needs Q >= 2, Q = 1 uses f32x2 over dimension pairs);
+//       1 = f32x2 over dimension pairs, 0 = scalar: only in builds with -DNN_AB_MATH (A/B measurements).
 template <class F>
 static cudaError_t qreg_dispatch(int q_sel, int math, F f)
 {
@@ -64,10 +85,15 @@ static cudaError_t qreg_dispatch(int q_sel, int math, F f)
         constexpr int QV = decltype(qc)::value;
         if constexpr (QV <= QD)
         {
+#ifdef NN_AB_MATH // A/B builds only: the shipped library holds the pair-packed kernels (and mode 1 for Q = 1)
             if (math == 0)
                 return f(qc, std::integral_constant<int, 0>{});
             if (math == 1 || QV == 1)
                 return f(qc, std::integral_constant<int, 1>{});
+#else
+            if (math != 2)
+                return cudaErrorInvalidValue;
+#endif
             return f(qc, std::integral_constant<int, (QV >= 2 ? 2 : 1)>{});
         }
         else
@@ -102,6 +128,76 @@ cudaError_t query_qreg<NN_K>(int q_sel, int math, LaunchInfo *info, int *tile_qu
     return qreg_dispatch(q_sel, math, [&](auto qc, auto pk) {
         return query_qreg_one<NN_K, decltype(qc)::value, 128, decltype(pk)::value>(info, tile_queries, tile_refs);
     });
+}
+
+// ---- phased query-register kernel ---------------------------------------------------------------
+template <int K, int Q>
+static cudaError_t launch_qflex_one(const QflexArgs &a, uint32_t qtiles, cudaStream_t st)
+{
+    auto kern = nn_qflex_kernel<K, Q, 128>;
+    static PerDeviceOnce once;
+    const cudaError_t e = once([&] {
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QregCfg<K>::SMEM);
+    });
+    if (e != cudaSuccess)
+        return e;
+    kern<<<qtiles * a.splits, 128, QregCfg<K>::SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int K, int Q>
+static cudaError_t query_qflex_one(FlexInfo *info)
+{
+    auto kern = nn_qflex_kernel<K, Q, 128>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QregCfg<K>::SMEM);
+    if (e != cudaSuccess)
+        return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess)
+        return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, QregCfg<K>::SMEM);
+    if (e != cudaSuccess)
+        return e;
+    info->regs = fa.numRegs;
+    info->smem = (int)QregCfg<K>::SMEM;
+    info->occ = occ;
+    info->ch = QregCfg<K>::CH;
+    info->g = Geo<K>::G;
+    info->tr = QregCfg<K>::TR;
+    return cudaSuccess;
+}
+
+template <class F>
+static cudaError_t qflex_dispatch(int q, F f)
+{
+    constexpr int QD = QregDefault<NN_K>::Q;
+    if (q == 2)
+        return f(std::integral_constant<int, 2>{});
+    if (q == 4)
+    {
+        if constexpr (QD >= 4)
+            return f(std::integral_constant<int, 4>{});
+    }
+    if (q == 8)
+    {
+        if constexpr (QD >= 8)
+            return f(std::integral_constant<int, 8>{});
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <>
+cudaError_t launch_qflex<NN_K>(int q, const QflexArgs &a, uint32_t qtiles, cudaStream_t st)
+{
+    return qflex_dispatch(q, [&](auto qc) { return launch_qflex_one<NN_K, decltype(qc)::value>(a, qtiles, st); });
+}
+
+template <>
+cudaError_t query_qflex<NN_K>(int q, FlexInfo *info)
+{
+    return qflex_dispatch(q, [&](auto qc) { return query_qflex_one<NN_K, decltype(qc)::value>(info); });
 }
 
 // ---- reference-register kernel ------------------------------------------------------------------
@@ -216,14 +312,12 @@ static cudaError_t launch_rtma_one(const RregArgs &a, dim3 grid, cudaStream_t st
     if ((a.mq_total + MQ - 1) / MQ != (int)grid.y || a.mq_total < 1)
         return cudaErrorInvalidValue;
     auto kern = nn_rtma_kernel<K, MQ, S::PT, S::NW, S::STAGES, S::MINB>;
-    static bool configured = false;
-    if (!configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::Cfg::smem(MQ));
-        if (e != cudaSuccess)
-            return e;
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    const cudaError_t e = once([&] {
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::Cfg::smem(MQ));
+    });
+    if (e != cudaSuccess)
+        return e;
     kern<<<grid, (S::NW + 1) * 32, S::Cfg::smem(MQ), st>>>(a);
     return cudaGetLastError();
 }

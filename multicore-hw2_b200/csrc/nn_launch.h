@@ -8,6 +8,26 @@
 namespace nnb200
 {
 
+#ifdef NN_AB_MATH
+constexpr bool kAbMath = true; // the scalar / dimension-pair math modes are compiled in (A/B builds)
+#else
+constexpr bool kAbMath = false;
+#endif
+
+// "Finish in the same launch": when `tickets` is non-null the CTAs of one ticket group (a query tile of
+// the query-register kernels, a pass of the few-query kernels) count themselves on tickets[group]
+// after folding their candidates; the LAST one to arrive reads the group's final keys, stores
+// results[i] = index (and/or keys_out[i] = key) and puts keys and ticket back into the start
+// state.  One launch then does what keys_init -> search -> keys_unpack did in three, and the key
+// array it folds into (the workspace) is left ready for the next search.  Replaces
+// `result[bx*m+by] = ind_s[0]` (core.cu:853-854) + the host reduce (core.cu:765-787).
+struct Finish
+{
+    unsigned int *tickets = nullptr;        // one counter per ticket group, all zero between launches
+    int *results = nullptr;                 // optional: int[m] nearest indices
+    unsigned long long *keys_out = nullptr; // optional: final packed keys (multi-GPU merge input)
+};
+
 struct QregArgs
 {
     const float *S;
@@ -20,6 +40,26 @@ struct QregArgs
     unsigned long long *keys;
     float neg_zero;           // must be -0.0f: run-time addend of the exact fma(d, d, -0) square
     int peer_keys;            // keys live in another GPU's memory: fold with system-scope atomics
+    Finish fin;               // ticket group = query tile (blockIdx.x / splits), `splits` CTAs each
+};
+
+// Phased query-register kernel (nn_qflex_kernel): 128 threads = ng query groups x np phases.
+struct QflexArgs
+{
+    const float *S;
+    const float *R;
+    int m;
+    uint32_t n;
+    uint32_t index_base;
+    uint32_t splits;         // reference splits per query tile
+    uint32_t refs_per_split; // multiple of np * CH references (the last split takes what is left)
+    uint32_t tile_queries;   // queries per query tile, <= ng * Q
+    uint32_t ng, np;         // ng * np <= 128
+    uint32_t tile_groups;    // reference groups per ring stage: a multiple of np * CH / G, <= TR / G
+    unsigned long long *keys;
+    float neg_zero;
+    int peer_keys;
+    Finish fin;              // ticket group = query tile, `splits` CTAs each
 };
 
 struct RregArgs
@@ -32,6 +72,7 @@ struct RregArgs
     unsigned long long *keys; // already offset to q0
     float neg_zero;           // must be -0.0f (see QregArgs)
     int peer_keys;            // see QregArgs
+    Finish fin;               // ticket group = pass (blockIdx.y), gridDim.x CTAs each; results/keys_out offset like keys
 };
 
 // ---- per-K launchers (defined in nn_kernels_k.cu) -----------------------------------------
@@ -46,6 +87,16 @@ template <int K>
 cudaError_t launch_qreg(int q_sel, int math, const QregArgs &a, uint32_t qtiles, cudaStream_t st);
 template <int K>
 cudaError_t query_qreg(int q_sel, int math, LaunchInfo *info, int *tile_queries, int *tile_refs);
+// q = 2, 4 or 8 queries per thread (8 only where kernel A has it); info: chunk (CH) and group (G) sizes, TR
+struct FlexInfo
+{
+    int regs, smem, occ;
+    int ch, g, tr;
+};
+template <int K>
+cudaError_t launch_qflex(int q, const QflexArgs &a, uint32_t qtiles, cudaStream_t st);
+template <int K>
+cudaError_t query_qflex(int q, FlexInfo *info);
 template <int K>
 cudaError_t launch_rreg(int mq, bool soa, const RregArgs &a, dim3 grid, cudaStream_t st);
 template <int K>

@@ -87,12 +87,61 @@ def repack_soa(R: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor
     return out
 
 
-def search(S: torch.Tensor, R: torch.Tensor) -> torch.Tensor:
-    """Device-resident equivalent of one cudaCallback: int32[m] nearest indices."""
-    keys = new_keys(S.numel() // S.shape[-1], S.device)
-    nearest_keys(S, R, keys)
-    return keys_unpack(keys)
+class Workspace:
+    """State of the one-launch search (include/nn_b200.h, section 2a): ticket counters + packed keys
+    for up to `m` queries, initialised once; every search leaves it initialised."""
+
+    def __init__(self, m: int, device=None):
+        self.m = int(m)
+        nbytes = lib().nn_b200_workspace_bytes(self.m)
+        self.buf = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=device or "cuda")
+        with torch.cuda.device(self.buf.device):
+            check(lib().nn_b200_workspace_init(self.buf.data_ptr(), self.m, _stream_ptr()))
+
+    @property
+    def keys(self) -> torch.Tensor:
+        """The workspace's key array as an int64 view (fold pieces into it with nearest_keys)."""
+        off = lib().nn_b200_workspace_keys(self.buf.data_ptr()) - self.buf.data_ptr()
+        return self.buf[off // 8: off // 8 + self.m]
+
+    def finish(self, out: torch.Tensor | None = None, keys_out: torch.Tensor | None = None, m: int | None = None):
+        m = self.m if m is None else m
+        if out is None and keys_out is None:
+            out = torch.empty(m, dtype=torch.int32, device=self.buf.device)
+        with torch.cuda.device(self.buf.device):
+            check(lib().nn_b200_workspace_finish(self.buf.data_ptr(), m, out.data_ptr() if out is not None else None,
+                                                 keys_out.data_ptr() if keys_out is not None else None, _stream_ptr()))
+        return out if out is not None else keys_out
+
+
+def search(S: torch.Tensor, R: torch.Tensor, ws: Workspace | None = None, out: torch.Tensor | None = None,
+           keys_out: torch.Tensor | None = None, index_base: int = 0) -> torch.Tensor:
+    """Device-resident equivalent of one cudaCallback in ONE kernel launch: int32[m] nearest indices
+    (and/or the final packed keys in `keys_out`).  Replaces transpose + cudaCallbackKernel + host reduce
+    (core.cu:726-787)."""
+    _chk(S, torch.float32, "S")
+    _chk(R, torch.float32, "R")
+    k = S.shape[-1]
+    m = S.numel() // k
+    n = R.numel() // k if R.numel() else 0
+    if R.numel() and R.shape[-1] != k:
+        raise ValueError("S and R disagree on k")
+    if ws is None:
+        ws = Workspace(m, S.device)
+    if ws.m < m:
+        raise ValueError("workspace too small for this many queries")
+    if out is None and keys_out is None:
+        out = torch.empty(m, dtype=torch.int32, device=S.device)
+    if out is not None:
+        _chk(out, torch.int32, "out")
+    if keys_out is not None:
+        _chk(keys_out, torch.int64, "keys_out")
+    with torch.cuda.device(S.device):
+        check(lib().nn_b200_search_device(k, m, n, S.data_ptr(), R.data_ptr(), index_base, ws.buf.data_ptr(),
+                                          out.data_ptr() if out is not None else None,
+                                          keys_out.data_ptr() if keys_out is not None else None, _stream_ptr()))
+    return out if out is not None else keys_out
 
 
 __all__ = ["KEY_INIT", "new_keys", "keys_init", "nearest_keys", "nearest_keys_soa", "keys_unpack", "repack_soa",
-           "search"]
+           "search", "Workspace"]

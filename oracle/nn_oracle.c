@@ -19,13 +19,25 @@
  * are part of the contract: IEEE round-to-nearest float sub/mul/add, no contraction to
  * FMA, no reassociation, strictly sequential accumulation over the dimensions.
  */
+#define _GNU_SOURCE
 #include <math.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+
+/* Host threads this process may run on (its CPU affinity), NOT omp_get_max_threads(): torchrun
+ * exports OMP_NUM_THREADS=1, which would make "all host threads" mean one on multi-GPU runs. */
+static int host_threads(void)
+{
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0)
+        return CPU_COUNT(&set);
+    return 1;
+}
 
 /* One query against the whole reference set.  Follows core.cu:39-56:
  *   start state (INFINITY, index 0)                                   core.cu:39-40
@@ -71,7 +83,7 @@ int nn_oracle_v0_mt(int k, int m, int n, const float *S, const float *R, int *ou
     int used = 1;
 #ifdef _OPENMP
     if (threads < 1)
-        threads = omp_get_max_threads();
+        threads = host_threads();
     if (threads > m)
         threads = m > 0 ? m : 1;
     used = threads;
@@ -100,7 +112,7 @@ float nn_oracle_sqdist(int k, const float *q, const float *r)
 void nn_oracle_keys(int k, int m, int n, const float *S, const float *R, uint64_t *keys)
 {
 #ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads())
 #endif
     for (int mInd = 0; mInd < m; ++mInd) {
         float d;

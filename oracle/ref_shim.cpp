@@ -10,9 +10,25 @@
 // queries are independent, core.cu:37).
 #include <stdlib.h>
 #include <string.h>
+#include <sched.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+
+// Host threads this process may run on.  Deliberately NOT omp_get_max_threads(): launchers such as
+// torchrun export OMP_NUM_THREADS=1, which would silently turn the "all host cores" baseline into a
+// single-thread one on multi-GPU runs.
+static int host_threads()
+{
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0)
+    {
+        const int c = CPU_COUNT(&set);
+        if (c > 0)
+            return c;
+    }
+    return 1;
+}
 
 namespace v0
 {
@@ -34,7 +50,7 @@ extern "C" int ref_v0_mt(int k, int m, int n, float *S, float *R, int *out, int 
     int used = 1;
 #ifdef _OPENMP
     if (threads < 1)
-        threads = omp_get_max_threads();
+        threads = host_threads();
     if (threads > m)
         threads = m > 0 ? m : 1;
     used = threads;

@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TA = json.load(open(os.path.join(GOLD, "ta_results.json")))
 REF = json.load(open(os.path.join(GOLD, "ref_v0_cases.json")))
 
-VARIANTS = {"auto": 0, "qreg": 1, "rreg": 2, "plain": 3, "rtma": 4}
+VARIANTS = {"auto": 0, "qreg": 1, "rreg": 2, "plain": 3, "rtma": 4, "qflex": 5}
 
 
 @pytest.fixture(scope="module")
@@ -53,7 +53,7 @@ def gpu_keys(nn, S, R, variant="auto", soa=False, index_base=0, q=0, math=2):
         nn.set_option("math", 2)
 
 
-@pytest.mark.parametrize("variant", ["auto", "qreg", "rreg", "plain", "rtma"])
+@pytest.mark.parametrize("variant", ["auto", "qreg", "rreg", "plain", "rtma", "qflex"])
 @pytest.mark.parametrize("case", REF["cases"], ids=lambda c: f"{c['kind']}-k{c['k']}-m{c['m']}-n{c['n']}")
 def test_reference_v0_fixture(nn, oracle, case, variant):
     """Indices equal the reference's own v0 outputs (fixture); keys equal the oracle's."""
@@ -63,13 +63,54 @@ def test_reference_v0_fixture(nn, oracle, case, variant):
     assert np.array_equal(keys, oracle.keys(S, R))
 
 
+@pytest.mark.parametrize("variant", ["auto", "qreg", "rreg", "plain", "rtma", "qflex"])
+def test_one_launch_search_reuses_its_workspace(nn, oracle, variant):
+    """nn_b200_search_device: search + merge + index store in one launch (the last CTA of every ticket
+    group finishes and restores the workspace).  One workspace serves every fixture case in turn --
+    any state left behind by a search would corrupt the next -- and returns indices, keys, or both."""
+    import torch
+    from multicore_hw2_b200 import device
+    big = max(c["m"] for c in REF["cases"])
+    ws = device.Workspace(big)
+    nn.set_option("variant", VARIANTS[variant])
+    try:
+        for i, case in enumerate(REF["cases"]):
+            S, R = cases.make(case["kind"], case["seed"], case["k"], case["m"], case["n"])
+            dS, dR = torch.from_numpy(S).cuda(), torch.from_numpy(R).cuda()
+            m = case["m"]
+            out = torch.full((m,), -7, dtype=torch.int32, device="cuda")
+            keys = torch.zeros(m, dtype=torch.int64, device="cuda")
+            mode = i % 3
+            device.search(dS, dR, ws, out=out if mode != 1 else None, keys_out=keys if mode != 0 else None)
+            if mode != 1:
+                assert out.cpu().tolist() == case["indices"], (case, variant)
+            if mode != 0:
+                assert np.array_equal(keys.cpu().numpy().view(np.uint64), oracle.keys(S, R)), (case, variant)
+        assert bool((ws.keys == device.KEY_INIT).all()) and int(ws.buf[:512].abs().sum()) == 0  # start state again
+        # pieces folded into the workspace's keys, then one finishing kernel
+        S, R = cases.make("duplicated", 77, 5, 300, 9001)
+        dS, dR = torch.from_numpy(S).cuda(), torch.from_numpy(R).cuda()
+        for b in (6000, 3000, 0):
+            device.nearest_keys(dS, dR[b:b + 3001], ws.keys[:300], b)
+        assert np.array_equal(ws.finish(m=300).cpu().numpy(), oracle.v0(S, R, threads=0))
+        assert bool((ws.keys == device.KEY_INIT).all())
+        # n = 0: v0's start state, index 0
+        assert device.search(dS, dR[:0], ws).cpu().tolist() == [0] * 300
+    finally:
+        nn.set_option("variant", 0)
+
+
 @pytest.mark.parametrize("case", [c for c in REF["cases"] if c["kind"] in ("twins", "quantized", "specials")],
                          ids=lambda c: f"{c['kind']}-k{c['k']}")
 def test_soa_path_and_other_math_modes(nn, oracle, case):
     S, R = cases.make(case["kind"], case["seed"], case["k"], case["m"], case["n"])
     want = oracle.keys(S, R)
     assert np.array_equal(gpu_keys(nn, S, R, soa=True), want)
-    for math in (0, 1):
+    for math in (0, 1):   # scalar / dimension-pair math: only in -DNN_AB_MATH builds of the library
+        try:
+            nn.set_option("math", math)
+        except nn.NNError:
+            continue
         assert np.array_equal(gpu_keys(nn, S, R, "qreg", math=math), want)
     for q in (1, 2):
         assert np.array_equal(gpu_keys(nn, S, R, "qreg", q=q), want)
@@ -112,6 +153,24 @@ def test_few_query_kernels_over_many_tiles(nn, oracle, variant, k, m, n):
     CTAs) and a ragged end; bit-exact keys against the oracle."""
     S, R = cases.make("duplicated", 5100 + k + m, k, m, n)
     assert np.array_equal(gpu_keys(nn, S, R, variant), oracle.keys(S, R))
+
+
+@pytest.mark.parametrize("k", list(range(3, 17)))
+def test_phased_query_register_kernel_layouts(nn, oracle, k):
+    """nn_qflex_kernel: 128 threads = query groups x reference phases.  Query counts that give very
+    different layouts (many phases / few, several query tiles, forced queries per thread), reference
+    counts with ragged rounds and several tiles per CTA, duplicated references across phases, tiles and
+    CTAs (lowest index must win); bit-exact keys against the oracle."""
+    for m, n, q in [(9, 70001, 0), (31, 40003, 2), (100, 50021, 0), (100, 3, 4), (130, 33333, 0), (257, 20011, 2),
+                    (300, 9973, 4), (17, 129, 0)]:
+        if q == 4 and k in (13, 15):
+            continue  # 4 queries per thread do not fit the register budget there (QregDefault)
+        S, R = cases.make("duplicated", 6100 + k + m, k, m, n)
+        assert np.array_equal(gpu_keys(nn, S, R, "qflex", q=q), oracle.keys(S, R)), (k, m, n, q)
+    S, R = cases.make("twins", 6200 + k, k, 100, 3000)
+    assert np.array_equal(gpu_keys(nn, S, R, "qflex"), oracle.keys(S, R))
+    S, R = cases.make("specials", 6300 + k, k, 77, 1000)
+    assert np.array_equal(gpu_keys(nn, S, R, "qflex"), oracle.keys(S, R))
 
 
 @pytest.mark.parametrize("k,n", [(3, 10007), (7, 4096), (8, 5001), (16, 3000), (13, 1)])
