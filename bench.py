@@ -129,6 +129,10 @@ class ClockSampler:
                 pass
             self._stop.wait(0.02)
 
+    def reset(self):
+        """Forget what was sampled so far (the warm-up): only the timed region counts."""
+        self.samples, self.reasons = [], set()
+
     def stop(self):
         self._stop.set()
         if self._t:
@@ -330,9 +334,12 @@ def roofline_of(k, m, n_local, kernel_ms, peaks, sms, plan, workload):
     return roof
 
 
-def device_leg(nn, k, m, n_total, steps, warmup, dev, world=1, rank=0, scaling="strong", seed=1000, sampler=None):
+def device_leg(nn, k, m, n_total, steps, warmup, dev, world=1, rank=0, scaling="strong", seed=1000, sampler=None,
+               merge="peer", peer=None):
     """K timed steps of the device-resident search on this rank's shard.  Returns a dict of raw timings
-    plus the tensors (queries, shard, result) for the later legs."""
+    plus the tensors (queries, shard, result) for the later legs.
+    merge (N > 1): "peer" = the exchange fused into the search kernels over NVLink peer memory (one launch
+    per rank; result on rank 0, as v8 leaves it on its host), "nccl" = search -> all-reduce(min) -> unpack."""
     import torch
     import torch.distributed as dist
     from multicore_hw2_b200 import device, sharded
@@ -351,6 +358,11 @@ def device_leg(nn, k, m, n_total, steps, warmup, dev, world=1, rank=0, scaling="
             e0.record()
         if world == 1:
             device.search(S, R, ws, out=out, index_base=begin)          # ONE launch
+        elif merge == "peer":
+            peer.search(S, R, begin, out)                               # ONE launch per rank; rank 0 gets `out`
+            if e1 is not None:
+                e1.record()
+                e2.record()
         else:
             device.search(S, R, ws, keys_out=keys, index_base=begin)    # search -> final keys of this shard
             if e1 is not None:
@@ -362,6 +374,8 @@ def device_leg(nn, k, m, n_total, steps, warmup, dev, world=1, rank=0, scaling="
         if e3 is not None:
             e3.record()
 
+    if sampler is not None:
+        sampler.start()  # (before the warm-up: starting NVML takes ~0.1 s of host time on this rank)
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
@@ -370,7 +384,7 @@ def device_leg(nn, k, m, n_total, steps, warmup, dev, world=1, rank=0, scaling="
         dist.barrier()
     torch.cuda.synchronize()
     if sampler is not None:
-        sampler.start()
+        sampler.reset()
     gc.disable()
     # one more untimed step AFTER the synchronize, so that the host is enqueueing ahead of the device
     # when the first timed step starts (right after a host sync every launch latency of the first
@@ -390,13 +404,13 @@ def device_leg(nn, k, m, n_total, steps, warmup, dev, world=1, rank=0, scaling="
     gc.enable()
     launches = nn.launch_count() - launches0
     step_ms = [e[0].elapsed_time(e[3]) for e in ev]
-    if world == 1:
+    if world == 1 or merge == "peer":
         kern_ms, merge_ms = list(step_ms), [0.0] * steps
     else:
         kern_ms = [e[0].elapsed_time(e[1]) for e in ev]
         merge_ms = [e[1].elapsed_time(e[2]) for e in ev]  # incl. waiting for the slowest rank
     return {"S": S, "R": R, "out": out, "begin": begin, "n_local": n_local, "step_ms": step_ms, "kern_ms": kern_ms,
-            "merge_ms": merge_ms, "launches": launches, "wall_s": t_wall,
+            "merge_ms": merge_ms, "launches": launches, "wall_s": t_wall, "merge": merge if world > 1 else None,
             "plan": nn.describe_plan(k, m, max(n_local, 1))}
 
 
@@ -499,6 +513,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-all-configs", action="store_true")
+    ap.add_argument("--merge", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = the exchange fused into the search kernels over NVLink peer memory (CUDA IPC, "
+                         "system-scope atomicMin into rank 0's keys); nccl = search -> all-reduce(min) -> unpack")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="strong (contract default): the workload's ONE reference set is sharded over the ranks "
                          "(v8, core.cu:875-883); weak: every rank owns the workload's n references")
@@ -543,8 +560,35 @@ def main():
     # clocks are sampled on rank 0 only: NVML queries take driver locks, and one poller per rank
     # delayed launches enough to show up as all-reduce skew
     sampler = ClockSampler(local if rank == 0 else -1)
-    leg = device_leg(nn, k, m, n_total, args.steps, args.warmup, dev, world, rank, args.scaling, sampler=sampler)
+    merge, peer, peer_note = args.merge, None, None
+    if world > 1 and merge == "peer":
+        try:
+            from multicore_hw2_b200 import sharded
+            peer = sharded.PeerMerge(m, group=host_group)
+        except Exception as e:  # no CUDA IPC between the ranks (not the case on an NVSwitch box): say so, use NCCL
+            peer_note = f"peer merge unavailable ({str(e)[:200]}): fell back to the NCCL all-reduce"
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            merge, peer = "nccl", None
+    leg = device_leg(nn, k, m, n_total, args.steps, args.warmup, dev, world, rank, args.scaling, sampler=sampler,
+                     merge=merge, peer=peer)
     clocks = sampler.stop()
+    nccl_leg = None
+    if world > 1 and merge == "peer":
+        # the same steps with the exchange as a collective, for comparison (fewer steps)
+        lg2 = device_leg(nn, k, m, n_total, max(3, min(args.steps, 10)), 3, dev, world, rank, args.scaling, merge="nccl")
+        t2 = torch.tensor([sum(lg2["step_ms"]) / len(lg2["step_ms"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        same = torch.tensor([1 if (rank != 0 or torch.equal(lg2["out"], leg["out"])) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        nccl_leg = {"ms_per_step": float(t2.item()), "steps": len(lg2["step_ms"]),
+                    "kernel_ms": sum(lg2["kern_ms"]) / len(lg2["kern_ms"]), "merge_ms": sum(lg2["merge_ms"]) / len(lg2["merge_ms"]),
+                    "same_result_as_peer_merge": bool(int(same.item())),
+                    "step": "search (final keys of the shard) -> ncclAllReduce(min, u64) -> keys_unpack"}
+        del lg2
+        if peer.error():
+            peer_note = "a device-side wait of the peer merge timed out"
     step_ms, kern_ms, merge_ms = leg["step_ms"], leg["kern_ms"], leg["merge_ms"]
     t = torch.tensor([sum(step_ms), sum(kern_ms) / len(kern_ms)], dtype=torch.float64, device=dev)
     t_max, t_min = t.clone(), t.clone()
@@ -581,7 +625,7 @@ def main():
             Sh = leg["S"].cpu().numpy()
             calls = max(1, min(args.steps, 5 if pairs_per_step > 2e11 else 20))
             e2e, results = e2e_leg(nn, k, m, n_total, Sh, Rh, calls, world)
-            results["device_resident" + ("_nccl_merge" if world > 1 else "")] = leg["out"].cpu().numpy()
+            results["device_resident" + (f"_{merge}_merge" if world > 1 else "")] = leg["out"].cpu().numpy()
             parity, parity_n = spot_check(k, m, Sh, Rh, results)
             e2e["matches_device_resident_result"] = bool(np.array_equal(results["cudaCallback"], leg["out"].cpu().numpy()))
         if world > 1:
@@ -645,21 +689,24 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_string(args.workload, args.scaling, world),
                        "k": k, "m": m, "n_total": n_total,
-                       "parallelism": (f"{world} reference shards of one set (strong scaling), one process per GPU, "
-                                       "NCCL all-reduce(min) of uint64 keys" if world > 1 and args.scaling == "strong"
-                                       else (f"reference shards x{world} (weak), NCCL all-reduce(min) of uint64 keys"
-                                             if world > 1 else "1 GPU")),
+                       "parallelism": (f"{world} reference shards of one set ({args.scaling} scaling), one process per GPU; merge: "
+                                       + ("inside the search kernels, system-scope u64 atomicMin into rank 0's keys over NVLink "
+                                          "peer memory (CUDA IPC), result on rank 0" if merge == "peer"
+                                          else "NCCL all-reduce(min) of uint64 keys") if world > 1 else "1 GPU"),
+                       "merge": merge if world > 1 else None, "merge_note": peer_note,
                        "l2": "flushed between steps (256 MiB written then 256 MiB read, outside the event window)",
                        "timing": "CUDA events per step on the launching stream, summed over the K steps, max over ranks; "
                                  "one untimed priming step between the synchronize and the first timed step",
                        "step": "one launch: nn_b200_search_device (search + merge + index store)" if world == 1 else
-                               "search (one launch, final keys of the shard) -> all-reduce(min) -> keys_unpack",
+                               ("one launch per rank: nn_b200_peer_search (search + cross-GPU merge + index store on rank 0)"
+                                if merge == "peer" else
+                                "search (one launch, final keys of the shard) -> all-reduce(min) -> keys_unpack"),
                        "plan": plan, "data": "uniform [0,1) float32, seeded"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "parity_spot_check": (all(parity.values()) if parity else None),
             "parity_detail": ({"oracle_queries": parity_n, "oracle": "oracle/nn_oracle.c v0 restatement, full reference set",
                                **parity} if parity else None),
-            "all_configs": all_cfg,
+            "all_configs": all_cfg, "nccl_merge": nccl_leg,
             "clocks": clocks, "wall_ms_per_step_incl_flush": 1e3 * wall_s / args.steps,
             "step_ms_min_max": [min(step_ms), max(step_ms)], "step_ms": [round(x, 4) for x in step_ms[:32]],
             "merge_ms": sum(merge_ms) / len(merge_ms),
@@ -669,6 +716,8 @@ def main():
         emit(line)
     if world > 1:
         dist.barrier(group=host_group)
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
 
 

@@ -149,6 +149,34 @@ NN_B200_API int nn_b200_index_info(const nn_b200_index *index, int *k, int64_t *
 NN_B200_API void nn_b200_index_destroy(nn_b200_index *index);
 
 /* ------------------------------------------------------------------------------------------
+ * 2c. Multi-PROCESS merge over NVLink peer memory (one process per GPU of one node).
+ *     v8 gathers the per-GPU candidates on the host and reduces them there (core.cu:925-957); with one
+ *     process per GPU the obvious replacement is search -> ncclAllReduce(min, u64) -> unpack.  Here the
+ *     exchange happens INSIDE the search kernels instead: rank 0 owns two alternating key arrays in
+ *     device memory that every other rank maps through CUDA IPC; every rank's search kernel folds its
+ *     shard's candidates into them with system-scope 64-bit atomicMin; the last CTA of a rank counts
+ *     the rank in; rank 0's last CTA waits for all ranks, stores the indices, restores the keys and
+ *     releases the buffer to the ranks (a flag in each rank's own memory).  One kernel launch per rank
+ *     and search, no collective, no host round trip.
+ *     Set-up: every rank calls _create, the 64-byte handles are exchanged by whatever transport the
+ *     host program has (torch.distributed in multicore_hw2_b200.sharded.PeerMerge), every rank calls
+ *     _attach with all of them in rank order.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct nn_b200_peer_merge nn_b200_peer_merge;
+#define NN_B200_PEER_HANDLE_BYTES 64
+NN_B200_API int nn_b200_peer_create(int m, int rank, int world, nn_b200_peer_merge **pm);
+NN_B200_API int nn_b200_peer_handle(const nn_b200_peer_merge *pm, void *handle, size_t len);
+NN_B200_API int nn_b200_peer_attach(nn_b200_peer_merge *pm, const void *handles_in_rank_order, size_t len);
+/* This rank's n references (device, AoS, global indices from index_base) against the m queries
+ * (device; the same on every rank).  Rank 0's d_results (device) receives the merged indices when its
+ * kernel completes; other ranks pass NULL.  Every rank calls it the same number of times.  Async. */
+NN_B200_API int nn_b200_peer_search(nn_b200_peer_merge *pm, int k, int m, int64_t n, const float *d_S, const float *d_R,
+                                    uint32_t index_base, int *d_results, void *stream);
+/* 1 if a wait inside one of this rank's kernels timed out (a rank missing or out of step). Synchronises. */
+NN_B200_API int nn_b200_peer_error(nn_b200_peer_merge *pm);
+NN_B200_API void nn_b200_peer_destroy(nn_b200_peer_merge *pm);
+
+/* ------------------------------------------------------------------------------------------
  * 3. Host-side helpers
  * ------------------------------------------------------------------------------------------ */
 

@@ -37,6 +37,13 @@ SIGNATURES = {
                                              ctypes.c_void_p]),
     "nn_b200_workspace_finish": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_void_p]),
+    "nn_b200_peer_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "nn_b200_peer_handle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "nn_b200_peer_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "nn_b200_peer_search": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]),
+    "nn_b200_peer_error": (ctypes.c_int, [ctypes.c_void_p]),
+    "nn_b200_peer_destroy": (None, [ctypes.c_void_p]),
     "nn_b200_shard_range": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                            ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "nn_b200_device_count": (ctypes.c_int, [ctypes.c_int64]),

@@ -18,6 +18,7 @@
 //     static WarmUP object, core.cu:1274);
 //   * no CPU fallback (core.cu:869-870 falls back to v0): without a GPU the call fails loudly.
 #include "../../include/nn_b200.h"
+#include "nn_kernels.cuh" // (templates only: finish_group for the arrive-only kernel of the multi-process merge)
 #include "nn_launch.h"
 
 #include <algorithm>
@@ -29,6 +30,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -39,7 +41,7 @@ using namespace nnb200;
 // ---------------------------------------------------------------------------------------------
 // errors, options, counters
 // ---------------------------------------------------------------------------------------------
-constexpr int kWsTickets = 1024; // ticket counters at the head of a search workspace (see nn_b200_workspace_bytes)
+constexpr int kWsTickets = 8192; // ticket counters at the head of a search workspace (see nn_b200_workspace_bytes)
 static thread_local std::string t_err;
 static std::atomic<int64_t> g_launches{0};
 
@@ -859,6 +861,26 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
         else
             (void)cudaGetLastError();
     }
+    // multi-process merge (struct PeerSync): the usual per-group finish, whose last CTA pushes the group's
+    // keys to rank 0 instead of unpacking them; the call's groups are counted to know when the rank is done
+    Finish peer_fin;
+    const bool peer_mode = fin && fin->peer.arrive != nullptr;
+    if (peer_mode)
+    {
+        unsigned int groups = 0;
+        if (p.variant == 1 || p.variant == 5)
+            groups = p.qtiles;
+        else if (p.variant == 2 || p.variant == 4)
+            groups = (unsigned int)(m / 8 + (m % 8 ? 1 : 0));
+        else
+            return fail(NN_B200_EINVAL, "the plain kernel has no in-kernel finish (multi-process merge)");
+        if (groups > (unsigned int)kWsTickets)
+            return fail(NN_B200_EINVAL, "m=%d needs %u ticket groups, more than the %d of a workspace", m, groups, kWsTickets);
+        peer_fin = *fin;
+        peer_fin.peer.num_groups = groups;
+        fin = &peer_fin;
+        peer = 0; // folds go to this rank's own workspace
+    }
     if (p.variant == 1)
     {
         QregArgs a;
@@ -928,11 +950,16 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
                 a.keys = keys + q0 + done * mq;
                 a.neg_zero = -0.0f;
                 a.peer_keys = peer;
+                a.q_first = q0 + done * mq;
                 if (use_fin)
                 {
+                    a.fin = *fin;
                     a.fin.tickets = fin->tickets + ticket_off;
-                    a.fin.results = fin->results ? fin->results + q0 + done * mq : nullptr;
-                    a.fin.keys_out = fin->keys_out ? fin->keys_out + q0 + done * mq : nullptr;
+                    if (!peer_mode)
+                    { // (multi-process mode: results belong to rank 0's final unpack of ALL queries)
+                        a.fin.results = fin->results ? fin->results + q0 + done * mq : nullptr;
+                        a.fin.keys_out = fin->keys_out ? fin->keys_out + q0 + done * mq : nullptr;
+                    }
                     ticket_off += py;
                 }
                 if (rtma)
@@ -1315,6 +1342,95 @@ int load_nccl()
 } // namespace
 
 // ---------------------------------------------------------------------------------------------
+// persistent host worker threads.  A host-entry call uses one thread per GPU (as v8 does with OpenMP,
+// core.cu:873) and, for pageable inputs, several staging threads per GPU; creating them per call cost
+// 50-100 us each -- a large part of a call that takes a millisecond.  The pools grow on demand, keep
+// their threads parked on a condition variable and are never destroyed (no static-destruction order
+// problems with threads that still wait).
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+class TaskGroup
+{
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int pending_ = 0;
+
+  public:
+    void add()
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        ++pending_;
+    }
+    void done()
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0)
+            cv_.notify_all();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return pending_ == 0; });
+    }
+    ~TaskGroup() { wait(); }
+};
+
+class WorkerPool
+{
+    struct State
+    {
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<std::function<void()>> queue;
+        int idle = 0, threads = 0;
+    };
+    State *st_ = new State; // leaked on purpose
+
+  public:
+    // runs f on a pool thread; g.wait() (or g's destructor) returns after it has finished
+    void submit(TaskGroup &g, std::function<void()> f)
+    {
+        g.add();
+        std::function<void()> task = [f = std::move(f), &g]() {
+            f();
+            g.done();
+        };
+        State *st = st_;
+        std::unique_lock<std::mutex> lk(st->mu);
+        st->queue.push_back(std::move(task));
+        if ((int)st->queue.size() > st->idle) // more queued tasks than parked threads: one more thread
+        {
+            ++st->threads;
+            lk.unlock();
+            std::thread([st]() {
+                for (;;)
+                {
+                    std::function<void()> job;
+                    {
+                        std::unique_lock<std::mutex> l2(st->mu);
+                        ++st->idle;
+                        st->cv.wait(l2, [&] { return !st->queue.empty(); });
+                        --st->idle;
+                        job = std::move(st->queue.front());
+                        st->queue.erase(st->queue.begin());
+                    }
+                    job();
+                }
+            }).detach();
+        }
+        else
+        {
+            lk.unlock();
+            st->cv.notify_one();
+        }
+    }
+};
+WorkerPool g_gpu_workers;   // one task per GPU of a call
+WorkerPool g_feed_workers;  // staging threads (submitted from within the GPU tasks: a pool of their own)
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
 // lazily created per-process context for the host entry point
 // ---------------------------------------------------------------------------------------------
 namespace
@@ -1521,11 +1637,13 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
     int64_t chunk_refs = std::max<int64_t>(4096, chunk_bytes / (int64_t)(k * sizeof(float)));
     chunk_refs = chunk_refs / 4096 * 4096; // keeps every chunk start 16-byte aligned and tile aligned
     // Chunk list.  Direct (pinned) path: the first chunks ramp up geometrically from 1/8 of the chunk
-    // size, so the search starts after a short first copy instead of a whole chunk's; staged path:
-    // uniform chunks (they are small already).
+    // size, so the search starts after a short first copy instead of a whole chunk's.
     std::vector<std::pair<int64_t, int64_t>> chunks; // (first reference, count) relative to the shard
     {
-        int64_t step = staged ? chunk_refs : std::max<int64_t>(4096, chunk_refs / 8 / 4096 * 4096);
+        // (staged path too: the first 4 MiB chunk alone is ~0.4 ms of single-thread memcpy before the
+        // GPU has anything to do; a ramp from 1/16 of the chunk size starts the search after ~30 us and
+        // the first, small chunks are staged by different threads in parallel)
+        int64_t step = std::max<int64_t>(4096, chunk_refs / (staged ? 16 : 8) / 4096 * 4096);
         for (int64_t off = 0; off < count;)
         {
             const int64_t cnt = std::min<int64_t>(step, count - off);
@@ -1546,25 +1664,25 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
     unsigned long long *keys = keys0 ? keys0 : c.dKeys;
     if (keys0)
         CU(cudaStreamWaitEvent(c.compute, keys_ready, 0));
-    if (!keys0)
+    if (!keys0 || dev == 0)
         c.ws_dirty = true;
     c.finished = false;
     CU(cudaStreamWaitEvent(c.compute, c.events[0], 0));
 
     const int feeders = staged ? (int)std::min<int64_t>(std::min<int64_t>(want_feeders, DevCtx::kMaxFeeders), (int64_t)nchunks) : 0;
-    std::vector<std::thread> fth;
     std::mutex fmu;
     std::condition_variable fcv;
     std::vector<char> recorded(nchunks, 0);
     int frc = NN_B200_OK;
     std::string ferr;
+    TaskGroup fgroup; // declared after everything the staging tasks touch: its destructor waits for them
     if (feeders > 0)
     {
         rc = ensure_staging(c, feeders, (size_t)chunk_refs * k * sizeof(float));
         if (rc)
             return rc;
         for (int t = 0; t < feeders; ++t)
-            fth.emplace_back([&, t]() {
+            g_feed_workers.submit(fgroup, [&, t]() {
                 auto bail = [&](cudaError_t e, size_t ci) {
                     std::lock_guard<std::mutex> lk(fmu);
                     if (frc == NN_B200_OK)
@@ -1601,16 +1719,6 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
                 }
             });
     }
-    struct Joiner
-    {
-        std::vector<std::thread> &t;
-        ~Joiner()
-        {
-            for (auto &x : t)
-                if (x.joinable())
-                    x.join();
-        }
-    } joiner{fth};
 
     for (size_t ci = 0; ci < nchunks; ++ci)
     {
@@ -1742,10 +1850,12 @@ static int run_sharded_body(int m, int gpus, Enqueue enqueue, int *results, int 
     if (p2p)
     {
         DevCtx &c0 = g_ctx.devs[0];
-        rc = ensure_dev(c0, 0, 16, 16, (size_t)std::max(m, 1), 1); // (its workspace is, or is being put, in the start state)
+        // (its workspace is, or is being put, in the start state.  It is marked dirty -- "a call is folding
+        // into it" -- by GPU 0's own enqueue, AFTER that enqueue's ensure_dev: marking it here would make
+        // that ensure_dev re-initialise the keys while the other GPUs are already folding into them)
+        rc = ensure_dev(c0, 0, 16, 16, (size_t)std::max(m, 1), 1);
         if (rc)
             return rc;
-        c0.ws_dirty = true;
         if (!c0.keys_ready)
             CU(cudaEventCreateWithFlags(&c0.keys_ready, cudaEventDisableTiming));
         CU(cudaEventRecord(c0.keys_ready, c0.compute));
@@ -1765,12 +1875,13 @@ static int run_sharded_body(int m, int gpus, Enqueue enqueue, int *results, int 
     else
     {
         // one host thread per GPU, as v8 does with OpenMP (core.cu:873): pageable copies block the
-        // issuing thread, so the shards are pushed in parallel
-        std::vector<std::thread> th;
-        for (int g = 0; g < gpus; ++g)
-            th.emplace_back(work, g);
-        for (auto &t : th)
-            t.join();
+        // issuing thread, so the shards are pushed in parallel (persistent pool threads; GPU 0's share
+        // runs on the calling thread)
+        TaskGroup grp;
+        for (int g = 1; g < gpus; ++g)
+            g_gpu_workers.submit(grp, [&work, g]() { work(g); });
+        work(0);
+        grp.wait();
     }
     for (int g = 0; g < gpus; ++g)
         if (rcs[g])
@@ -1946,11 +2057,11 @@ extern "C" int nn_b200_index_create(int k, int n, const float *R, int num_gpus, 
         load(0);
     else
     {
-        std::vector<std::thread> th;
-        for (int g = 0; g < gpus; ++g)
-            th.emplace_back(load, g);
-        for (auto &t : th)
-            t.join();
+        TaskGroup grp;
+        for (int g = 1; g < gpus; ++g)
+            g_gpu_workers.submit(grp, [&load, g]() { load(g); });
+        load(0);
+        grp.wait();
     }
     cudaSetDevice(prev_dev);
     for (int g = 0; g < gpus; ++g)
@@ -2107,7 +2218,7 @@ extern "C" int nn_b200_index_search(nn_b200_index *ix, int m, const float *S, in
                            unsigned long long *keys = keys0 ? keys0 : c.dKeys;
                            if (keys0)
                                CU(cudaStreamWaitEvent(c.compute, keys_ready, 0));
-                           if (!keys0)
+                           if (!keys0 || g == 0)
                                c.ws_dirty = true;
                            c.finished = false;
                            CU(cudaStreamWaitEvent(c.compute, c.events[0], 0));
@@ -2132,6 +2243,198 @@ extern "C" int nn_b200_index_search(nn_b200_index *ix, int m, const float *S, in
                            return NN_B200_OK;
                        },
                        results);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-process merge over NVLink peer memory: one process per GPU (torchrun ranks), rank 0 owns the
+// keys.  The exchange step of the sharded search (the reference's host-side gather + reduce,
+// core.cu:925-957; one ncclAllReduce(min, u64) in the NCCL driver) happens INSIDE the search kernels:
+// see struct PeerSync (nn_launch.h) and peer_finish (nn_kernels.cuh).
+// Block layout, identical on every rank (only rank 0's keys / arrive are used):
+//   [0] done  [64] groups_done  [128] error  [192] arrive[2]  [256] keys[2][m]  [..] this rank's search workspace
+// ---------------------------------------------------------------------------------------------
+struct nn_b200_peer_merge
+{
+    int m = 0, rank = 0, world = 0, dev = 0;
+    unsigned char *block = nullptr;          // this rank's block (cudaMalloc)
+    cudaIpcMemHandle_t handle{};
+    std::vector<unsigned char *> mapped;     // by rank: peer blocks opened here (rank 0: all; others: rank 0's)
+    unsigned int **d_done_peers = nullptr;   // rank 0: device array of the other ranks' done flags
+    unsigned int step = 0;
+    bool attached = false;
+};
+static size_t peer_ws_offset(int m) { return (256 + (size_t)2 * (size_t)std::max(m, 1) * 8 + 255) / 256 * 256; }
+static size_t peer_block_bytes(int m) { return peer_ws_offset(m) + nn_b200_workspace_bytes(std::max(m, 1)); }
+
+__global__ void nn_peer_arrive_kernel(const Finish f)
+{ // a rank whose shard is empty still has to be counted (one CTA, nothing folded)
+    finish_group(f, nullptr, 0, 1, 0, 0);
+}
+
+extern "C" void nn_b200_peer_destroy(nn_b200_peer_merge *pm)
+{
+    if (!pm)
+        return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(pm->dev);
+    cudaDeviceSynchronize();
+    for (unsigned char *p : pm->mapped)
+        if (p)
+            cudaIpcCloseMemHandle(p);
+    if (pm->d_done_peers)
+        cudaFree(pm->d_done_peers);
+    if (pm->block)
+        cudaFree(pm->block);
+    cudaSetDevice(prev);
+    (void)cudaGetLastError();
+    delete pm;
+}
+
+extern "C" int nn_b200_peer_create(int m, int rank, int world, nn_b200_peer_merge **out)
+{
+    if (m < 0 || world < 1 || rank < 0 || rank >= world || !out)
+        return fail(NN_B200_EINVAL, "bad peer_create arguments");
+    *out = nullptr;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    DevInfo di;
+    int rc = dev_info(dev, &di);
+    if (rc)
+        return rc;
+    nn_b200_peer_merge *pm = new nn_b200_peer_merge;
+    pm->m = m;
+    pm->rank = rank;
+    pm->world = world;
+    pm->dev = dev;
+    pm->mapped.assign(world, nullptr);
+    auto bail = [&](int code) {
+        nn_b200_peer_destroy(pm);
+        return code;
+    };
+    const size_t bytes = peer_block_bytes(m);
+    if (cudaMalloc(&pm->block, bytes) != cudaSuccess)
+        return bail(fail(NN_B200_ECUDA, "cudaMalloc of the peer block failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (cudaMemset(pm->block, 0, 256) != cudaSuccess)
+        return bail(fail(NN_B200_ECUDA, "cudaMemset failed"));
+    rc = nn_b200_keys_init(reinterpret_cast<uint64_t *>(pm->block + 256), 2 * std::max(m, 1), nullptr);
+    if (!rc)
+        rc = nn_b200_workspace_init(pm->block + peer_ws_offset(m), std::max(m, 1), nullptr);
+    if (rc)
+        return bail(rc);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&pm->handle, pm->block) != cudaSuccess)
+        return bail(fail(NN_B200_ECUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = pm;
+    return NN_B200_OK;
+}
+
+extern "C" int nn_b200_peer_handle(const nn_b200_peer_merge *pm, void *handle, size_t len)
+{
+    if (!pm || !handle || len < sizeof(cudaIpcMemHandle_t))
+        return fail(NN_B200_EINVAL, "peer_handle needs a %zu-byte buffer", sizeof(cudaIpcMemHandle_t));
+    memcpy(handle, &pm->handle, sizeof(cudaIpcMemHandle_t));
+    return NN_B200_OK;
+}
+
+// handles: world x 64 bytes, the result of nn_b200_peer_handle on every rank, in rank order
+extern "C" int nn_b200_peer_attach(nn_b200_peer_merge *pm, const void *handles, size_t len)
+{
+    if (!pm || !handles || len < (size_t)pm->world * sizeof(cudaIpcMemHandle_t))
+        return fail(NN_B200_EINVAL, "peer_attach needs world x %zu bytes", sizeof(cudaIpcMemHandle_t));
+    if (pm->attached)
+        return fail(NN_B200_EINVAL, "already attached");
+    CU(cudaSetDevice(pm->dev));
+    const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(handles);
+    auto open = [&](int r) -> int {
+        void *p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h[r], cudaIpcMemLazyEnablePeerAccess));
+        pm->mapped[r] = reinterpret_cast<unsigned char *>(p);
+        return NN_B200_OK;
+    };
+    if (pm->rank == 0)
+    {
+        std::vector<unsigned int *> flags;
+        for (int r = 1; r < pm->world; ++r)
+        {
+            const int rc = open(r);
+            if (rc)
+                return rc;
+            flags.push_back(reinterpret_cast<unsigned int *>(pm->mapped[r])); // [0] = that rank's done flag
+        }
+        if (!flags.empty())
+        {
+            CU(cudaMalloc(&pm->d_done_peers, flags.size() * sizeof(unsigned int *)));
+            CU(cudaMemcpy(pm->d_done_peers, flags.data(), flags.size() * sizeof(unsigned int *), cudaMemcpyHostToDevice));
+        }
+    }
+    else
+    {
+        const int rc = open(0);
+        if (rc)
+            return rc;
+    }
+    pm->attached = true;
+    return NN_B200_OK;
+}
+
+// One sharded search: this rank's n references (global indices from index_base) against the m queries;
+// rank 0's d_results receives the merged indices (other ranks pass NULL).  Every rank must call it the
+// same number of times.  Asynchronous on `stream`.
+extern "C" int nn_b200_peer_search(nn_b200_peer_merge *pm, int k, int m, int64_t n, const float *d_S, const float *d_R,
+                                   uint32_t index_base, int *d_results, void *stream)
+{
+    if (!pm || !pm->attached)
+        return fail(NN_B200_EINVAL, "peer merge not attached");
+    int rc = check_shape(k, m, n);
+    if (rc)
+        return rc;
+    if (m < 1 || m > pm->m)
+        return fail(NN_B200_EINVAL, "m=%d outside 1..%d of this peer merge", m, pm->m);
+    if (pm->rank == 0 && !d_results)
+        return fail(NN_B200_EINVAL, "rank 0 needs a result buffer");
+    unsigned char *b0 = pm->rank == 0 ? pm->block : pm->mapped[0];
+    void *ws = pm->block + peer_ws_offset(pm->m); // this rank's own workspace: the folds stay on this GPU
+    Finish fin;
+    fin.tickets = ws_tickets(ws);
+    fin.results = pm->rank == 0 ? d_results : nullptr;
+    fin.peer.groups_done = reinterpret_cast<unsigned int *>(pm->block + 64);
+    fin.peer.keys = reinterpret_cast<unsigned long long *>(b0 + 256) + (size_t)(pm->step & 1u) * (size_t)pm->m;
+    fin.peer.arrive = reinterpret_cast<unsigned int *>(b0 + 192);
+    fin.peer.done_local = reinterpret_cast<unsigned int *>(pm->block);
+    fin.peer.done_peers = pm->d_done_peers;
+    fin.peer.error = reinterpret_cast<unsigned int *>(pm->block + 128);
+    fin.peer.step = pm->step;
+    fin.peer.world = (unsigned int)pm->world;
+    fin.peer.rank = (unsigned int)pm->rank;
+    fin.peer.m = m;
+    bool done = false;
+    if (n > 0)
+    {
+        rc = nearest_keys_impl(k, m, n, d_S, d_R, index_base, ws_keys(ws), stream, false, 0, &fin, &done);
+        if (rc)
+            return rc;
+        if (!done)
+            return fail(NN_B200_EINVAL, "this plan has no in-kernel finish");
+    }
+    if (!done)
+    { // empty shard: be counted all the same (one group, nothing to push)
+        fin.peer.num_groups = 1;
+        nn_peer_arrive_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(fin);
+        CU(cudaGetLastError());
+        g_launches++;
+    }
+    pm->step++;
+    return NN_B200_OK;
+}
+
+// 1 if a wait inside a kernel of this rank timed out (a rank missing or out of step), else 0.  Synchronises.
+extern "C" int nn_b200_peer_error(nn_b200_peer_merge *pm)
+{
+    if (!pm)
+        return fail(NN_B200_EINVAL, "null peer merge");
+    unsigned int e = 0;
+    CU(cudaMemcpy(&e, pm->block + 128, sizeof e, cudaMemcpyDeviceToHost));
+    return (int)e;
 }
 
 extern "C" void nn_b200_cudaCallback(int k, int m, int n, float *searchPoints, float *referencePoints, int **results)

@@ -74,6 +74,15 @@
 #ifndef NN_QREG_PREFETCH
 #define NN_QREG_PREFETCH 1 // query-register kernel: load the next reference group while computing the current one
 #endif
+#ifndef NN_QFLEX_UNROLL_Q8
+#define NN_QFLEX_UNROLL_Q8 1 // phased query-register kernel: chunks unrolled in the tile loop, by queries per thread
+#endif
+#ifndef NN_QFLEX_UNROLL_Q4
+#define NN_QFLEX_UNROLL_Q4 2
+#endif
+#ifndef NN_QFLEX_UNROLL_Q2
+#define NN_QFLEX_UNROLL_Q2 4
+#endif
 #ifndef NN_QREG_REGCAP_LOW
 #define NN_QREG_REGCAP_LOW 0 // 1: always compile the query-register kernel for 4 CTAs/SM (128 regs)
 #endif
@@ -123,9 +132,101 @@ __device__ __forceinline__ void cta_bar()
         asm volatile("bar.sync %0, %1;" ::"n"(BAR_ID), "n"(BAR_THREADS) : "memory");
 }
 
+// ---- multi-process merge (struct PeerSync) ----------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Spins (one thread) until *flag >= target; gives up after about a minute and raises the error flag, so
+// that a rank that never shows up cannot hang the GPU for good (ranks may well be seconds apart: context
+// creation, lazy code loading, host-side work between searches).
+__device__ __forceinline__ void peer_spin(const unsigned int *flag, unsigned int target, unsigned int *error)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < target)
+    {
+        __nanosleep(64);
+        if (clock64() - t0 > 120000000000ll)
+        {
+            if (error)
+                atomicExch(error, 1u);
+            break;
+        }
+    }
+}
+
+// The last CTA of a ticket group in multi-process mode (all its threads): push the group's final keys
+// from this rank's workspace into rank 0's buffer, restore the workspace, count the group; the last
+// group counts the rank in, and on rank 0 waits for every rank and finishes the search.
+// `keys` = this rank's workspace keys (already offset like the launch's queries), `q_abs` = index of
+// the group's first query in the whole query set.
+template <int BAR_ID, int BAR_THREADS>
+__device__ __forceinline__ void peer_push_group(const Finish &f, unsigned long long *keys, int q_begin, int q_count,
+                                                int q_abs)
+{
+    const PeerSync &p = f.peer;
+    __shared__ uint32_t s_role; // 0: nothing more to do; 1: rank 0, last group of the call
+    const int nthr = BAR_ID == 0 ? (int)blockDim.x : BAR_THREADS;
+    const unsigned int buf = p.step & 1u;
+    // the buffer was last used by search step-2, which rank 0 must have consumed
+    if (p.step >= 2u && threadIdx.x == 0)
+        peer_spin(p.done_local, p.step - 1u, p.error);
+    cta_bar<BAR_ID, BAR_THREADS>();
+    for (int i = threadIdx.x; i < q_count; i += nthr)
+    {
+        const unsigned long long key = __ldcg(keys + q_begin + i);
+        if (key != KEY_INIT)
+            atomicMin_system(p.keys + q_abs + i, key);
+        __stcg(keys + q_begin + i, KEY_INIT);
+    }
+    cta_bar<BAR_ID, BAR_THREADS>();
+    if (threadIdx.x == 0)
+    {
+        __threadfence_system(); // the pushes (observed through the barrier) are out before the group is counted
+        const bool last = atomicAdd(p.groups_done, 1u) == p.num_groups - 1u;
+        if (last)
+        {
+            *p.groups_done = 0u; // every group of the call has pushed: ready for the next call
+            __threadfence_system();
+            atomicAdd_system(p.arrive + buf, 1u);
+        }
+        s_role = (last && p.rank == 0u) ? 1u : 0u;
+    }
+    cta_bar<BAR_ID, BAR_THREADS>();
+    if (s_role == 0u)
+        return;
+    if (threadIdx.x == 0)
+        peer_spin(p.arrive + buf, p.world, p.error); // every rank's shard is in
+    cta_bar<BAR_ID, BAR_THREADS>();
+    for (int i = threadIdx.x; i < p.m; i += nthr)
+    {
+        const unsigned long long key = __ldcg(p.keys + i);
+        if (f.results)
+            f.results[i] = (int)(unsigned int)(key & 0xffffffffull);
+        if (f.keys_out)
+            f.keys_out[i] = key;
+        __stcg(p.keys + i, KEY_INIT);
+    }
+    cta_bar<BAR_ID, BAR_THREADS>();
+    if (threadIdx.x == 0)
+    {
+        p.arrive[buf] = 0u;
+        __threadfence_system(); // the restored keys and counter precede the announcement
+        for (unsigned int r = 0; r + 1u < p.world; ++r)
+            st_release_sys(p.done_peers[r], p.step + 1u);
+        st_release_sys(p.done_local, p.step + 1u);
+    }
+}
+
 template <int BAR_ID = 0, int BAR_THREADS = 0>
 __device__ __forceinline__ void finish_group(const Finish &f, unsigned long long *keys, uint32_t group,
-                                             uint32_t expected, int q_begin, int q_count)
+                                             uint32_t expected, int q_begin, int q_count, int q_abs = -1)
 {
     if (f.tickets == nullptr) // (uniform over the grid)
         return;
@@ -137,21 +238,25 @@ __device__ __forceinline__ void finish_group(const Finish &f, unsigned long long
         uint32_t t;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(f.tickets + group) : "memory");
         s_last = (t == expected - 1u) ? 1u : 0u;
+        if (s_last)
+            f.tickets[group] = 0u;
     }
     cta_bar<BAR_ID, BAR_THREADS>();
-    if (s_last)
+    if (!s_last)
+        return;
+    if (f.peer.arrive != nullptr)
+    { // multi-process mode (uniform over the grid)
+        peer_push_group<BAR_ID, BAR_THREADS>(f, keys, q_begin, q_count, q_abs < 0 ? q_begin : q_abs);
+        return;
+    }
+    for (int i = threadIdx.x; i < q_count; i += nthr)
     {
-        for (int i = threadIdx.x; i < q_count; i += nthr)
-        {
-            const unsigned long long key = __ldcg(keys + q_begin + i);
-            if (f.results)
-                f.results[q_begin + i] = (int)(unsigned int)(key & 0xffffffffull);
-            if (f.keys_out)
-                f.keys_out[q_begin + i] = key;
-            __stcg(keys + q_begin + i, KEY_INIT);
-        }
-        if (threadIdx.x == 0)
-            f.tickets[group] = 0u;
+        const unsigned long long key = __ldcg(keys + q_begin + i);
+        if (f.results)
+            f.results[q_begin + i] = (int)(unsigned int)(key & 0xffffffffull);
+        if (f.keys_out)
+            f.keys_out[q_begin + i] = key;
+        __stcg(keys + q_begin + i, KEY_INIT);
     }
 }
 
@@ -776,7 +881,7 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, 2>()) nn_qflex_kernel(cons
 {
     using C = QregCfg<K>;
     constexpr int G = Geo<K>::G, F4 = Geo<K>::F4, CH = C::CH, CHG = CH / G, STAGES = C::STAGES;
-    constexpr int UNR = Q >= 8 ? 1 : (Q >= 4 ? 2 : 4);
+    constexpr int UNR = Q >= 8 ? NN_QFLEX_UNROLL_Q8 : (Q >= 4 ? NN_QFLEX_UNROLL_Q4 : NN_QFLEX_UNROLL_Q2);
     static_assert(CH % 2 == 0 && CH % G == 0, "chunks are whole groups and an even number of points");
     static_assert((size_t)NT * Q * 8 <= (size_t)STAGES * C::TILE_BYTES, "the phase exchange reuses the ring");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1225,7 +1330,7 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
         if (kmin < (KEY_INIT | NO_REF))
             fold_key(a.keys + q0 + tid, kmin, a.peer_keys);
     }
-    finish_group(a.fin, a.keys, (uint32_t)pass, gridDim.x, q0, valid_q);
+    finish_group(a.fin, a.keys, (uint32_t)pass, gridDim.x, q0, valid_q, a.q_first + q0);
 }
 
 // =============================================================================================
@@ -1746,7 +1851,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) nn_rtma_kernel(const Rreg
         if (kmin != KEY_NONE)
             fold_key(a.keys + q0 + tid, kmin, a.peer_keys);
     }
-    finish_group<1, NTC>(a.fin, a.keys, (uint32_t)pass, gridDim.x, q0, valid_q);
+    finish_group<1, NTC>(a.fin, a.keys, (uint32_t)pass, gridDim.x, q0, valid_q, a.q_first + q0);
 }
 
 // =============================================================================================

@@ -21,11 +21,33 @@ constexpr bool kAbMath = false;
 // state.  One launch then does what keys_init -> search -> keys_unpack did in three, and the key
 // array it folds into (the workspace) is left ready for the next search.  Replaces
 // `result[bx*m+by] = ind_s[0]` (core.cu:853-854) + the host reduce (core.cu:765-787).
+// Multi-PROCESS merge over NVLink peer memory (one process per GPU, nn_b200_peer_*).  Every rank's
+// search kernel first folds into the rank's OWN key workspace (GPU-scope atomics, as on one GPU); the
+// last CTA of every ticket group then pushes the group's final keys into rank 0's key array (CUDA-IPC
+// mapped) with ONE system-scope atomicMin per query, and the last group to do so counts the rank in
+// on `arrive`.  Rank 0's last CTA waits for all ranks, stores the indices, restores the keys and tells
+// every rank -- by a flag in THAT rank's memory -- how many searches are finished, which is what lets
+// a fast rank push search s only after search s-2 (same key buffer: two alternate) has been consumed.
+// No collective launch, no host round trip, m remote atomics per rank and search.
+struct PeerSync
+{
+    unsigned long long *keys = nullptr;        // rank 0's memory: this search's key buffer (m keys; two alternate)
+    unsigned int *arrive = nullptr;            // rank 0's memory: [2] ranks folded, per key buffer
+    unsigned int *done_local = nullptr;        // this rank's memory: searches finished by rank 0
+    unsigned int *const *done_peers = nullptr; // rank 0 only: the other ranks' flags (peer-mapped), world-1 of them
+    unsigned int *error = nullptr;             // this rank's memory: set when a wait timed out
+    unsigned int *groups_done = nullptr;       // this rank's memory: ticket groups of this call that have pushed
+    unsigned int num_groups = 0;               // ticket groups of this call over all its launches
+    unsigned int step = 0, world = 0, rank = 0;
+    int m = 0;                                 // queries (rank 0 unpacks all of them)
+};
+
 struct Finish
 {
     unsigned int *tickets = nullptr;        // one counter per ticket group, all zero between launches
     int *results = nullptr;                 // optional: int[m] nearest indices
     unsigned long long *keys_out = nullptr; // optional: final packed keys (multi-GPU merge input)
+    PeerSync peer;                          // peer.arrive != nullptr: multi-process mode (results/keys_out: rank 0's)
 };
 
 struct QregArgs
@@ -67,6 +89,7 @@ struct RregArgs
     const float *S;   // queries of this launch (already offset to its first query)
     const float *R;
     int mq_total;     // queries covered by this launch: gridDim.y = ceil(mq_total / MQ) passes
+    int q_first = 0;  // index of the launch's first query in the whole query set (multi-process merge)
     uint32_t n;
     uint32_t index_base;
     unsigned long long *keys; // already offset to q0
