@@ -75,7 +75,7 @@ struct Options
     std::atomic<int64_t> h2d_chunk_bytes{16 << 20};
     std::atomic<int64_t> waves{8};           // qreg: most CTA waves considered
     std::atomic<int64_t> stage_threads{-1};  // pageable inputs: host threads staging into pinned buffers (-1 auto, 0 off)
-    std::atomic<int64_t> stage_min_bytes{8 << 20}; // pageable reference sets from this size on go through the staging threads
+    std::atomic<int64_t> stage_min_bytes{4 << 20}; // pageable reference sets from this size on go through the staging threads
     std::atomic<int64_t> index_graph{1};     // resident index on one GPU: replay a captured CUDA graph for small batches
     std::atomic<int64_t> p2p_merge{1};       // multi-GPU host entry: 1 fold into GPU 0's keys over NVLink, 0 NCCL all-reduce
     std::atomic<int64_t> auto_gpus{1};       // host entry without an explicit GPU count: 1 = plan_gpus decides, 0 = all visible
@@ -1619,11 +1619,11 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
     const size_t bytesS = (size_t)m * k * sizeof(float);
     const size_t bytesR = (size_t)count * k * sizeof(float);
     // Pageable source (what the reference's harness passes): a cudaMemcpyAsync from it is staged by
-    // the driver on one thread at ~11 GB/s.  From 8 MiB on, `feeders` host threads instead copy
+    // the driver on one thread at ~11 GB/s.  From 4 MiB on, `feeders` host threads instead copy
     // alternate 4 MiB chunks into their own pinned double buffers and push them on their own
     // streams, so host copy, DMA and the search of earlier chunks all overlap.  Measured on the B200
     // box (16 cores), 2 GiB reference set: 193 ms (driver) -> 44 ms with 8 threads; pinned: 39 ms.
-    // Threshold: 8 MiB.  (Round 1 staged from 128 MiB on; BASELINE config 2's 64 MiB of malloc'ed
+    // Threshold: 4 MiB.  (Round 1 staged from 128 MiB on; BASELINE config 2's 64 MiB of malloc'ed
     // references then took the driver path, ~6 ms -- as long as its search -- against 1.3 ms pinned.)
     int64_t want_feeders = g_opt.stage_threads.load();
     if (want_feeders < 0)
@@ -1632,10 +1632,22 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
                            : 0;
     const bool staged = want_feeders > 0 && count > 0 && is_pageable(R);
     int64_t chunk_bytes = g_opt.h2d_chunk_bytes.load();
+    // Staged path: 4 MiB chunks, ramping up -- unless the whole shard is only a few chunks: then every
+    // staging thread gets ONE equal share (one thread copies at ~10 GB/s, so an 8 MiB set cut into
+    // 0.25 .. 4 MiB chunks had its last 4 MiB chunk alone take 0.4 ms; many small chunks cost more in
+    // launches and driver calls than they overlap: measured 0.83 / 1.38 ms for 8 MiB with 6 / 16 chunks).
+    bool staged_even = false;
     if (staged)
+    {
         chunk_bytes = std::min<int64_t>(chunk_bytes, 4 << 20);
-    int64_t chunk_refs = std::max<int64_t>(4096, chunk_bytes / (int64_t)(k * sizeof(float)));
-    chunk_refs = chunk_refs / 4096 * 4096; // keeps every chunk start 16-byte aligned and tile aligned
+        if ((int64_t)bytesR < 2 * want_feeders * chunk_bytes)
+        {
+            staged_even = true;
+            chunk_bytes = ((int64_t)bytesR + want_feeders - 1) / want_feeders;
+        }
+    }
+    int64_t chunk_refs = std::max<int64_t>(4096, (chunk_bytes + (int64_t)(k * sizeof(float)) - 1) / (int64_t)(k * sizeof(float)));
+    chunk_refs = (chunk_refs + (staged_even ? 4095 : 0)) / 4096 * 4096; // keeps every chunk start 16-byte aligned and tile aligned
     // Chunk list.  Direct (pinned) path: the first chunks ramp up geometrically from 1/8 of the chunk
     // size, so the search starts after a short first copy instead of a whole chunk's.
     std::vector<std::pair<int64_t, int64_t>> chunks; // (first reference, count) relative to the shard
@@ -1643,7 +1655,7 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
         // (staged path too: the first 4 MiB chunk alone is ~0.4 ms of single-thread memcpy before the
         // GPU has anything to do; a ramp from 1/16 of the chunk size starts the search after ~30 us and
         // the first, small chunks are staged by different threads in parallel)
-        int64_t step = std::max<int64_t>(4096, chunk_refs / (staged ? 16 : 8) / 4096 * 4096);
+        int64_t step = staged_even ? chunk_refs : std::max<int64_t>(4096, chunk_refs / (staged ? 16 : 8) / 4096 * 4096);
         for (int64_t off = 0; off < count;)
         {
             const int64_t cnt = std::min<int64_t>(step, count - off);

@@ -83,6 +83,9 @@
 #ifndef NN_QFLEX_UNROLL_Q2
 #define NN_QFLEX_UNROLL_Q2 4
 #endif
+#ifndef NN_QTILE_FASTEST
+#define NN_QTILE_FASTEST 0 // CTA order of the query-register kernels: 1 = query tile fastest (A/B: see nn_qreg_kernel)
+#endif
 #ifndef NN_QREG_REGCAP_LOW
 #define NN_QREG_REGCAP_LOW 0 // 1: always compile the query-register kernel for 4 CTAs/SM (128 regs)
 #endif
@@ -568,8 +571,20 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);
 
     const int tid = threadIdx.x;
+    // CTA order: reference split fastest.  With several waves (BASELINE config 4: 128 query tiles x 37
+    // splits = 8 waves) every wave then re-streams the reference set from HBM: 8.9 GB of DRAM reads for a
+    // 1.07 GB set (ncu r02_cfg4_qreg) -- 6 GB/s on average, 0.1% of the HBM bandwidth of an FP32-bound
+    // kernel.  The other order (query tile fastest: resident CTAs cover ALL tiles of a few splits) cuts
+    // that to 2.4 GB at an L2 hit rate of 96.7% but measured 1.3% SLOWER at configs 4 and 2 and 2% at
+    // k = 8, m = 65536 (128 CTAs in lockstep on the same lines of one L2 slice), so it stays an A/B switch.
+#if NN_QTILE_FASTEST
+    const uint32_t qtiles = gridDim.x / a.splits;
+    const uint32_t qtile = blockIdx.x % qtiles;
+    const uint32_t split = blockIdx.x / qtiles;
+#else
     const uint32_t split = blockIdx.x % a.splits;
     const uint32_t qtile = blockIdx.x / a.splits;
+#endif
     // This CTA's references: [r0, r1).  r0 is a multiple of 8 points (a whole chunk, 16-byte aligned for every
     // k); whole chunks [r0, r1c) stream through the TMA ring in tiles of up to TR points, and the
     // ragged end of the reference set (< CH points, last split only) is handled after the loop.
@@ -889,8 +904,15 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, 2>()) nn_qflex_kernel(cons
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);
 
     const int tid = threadIdx.x;
+    // CTA order: see nn_qreg_kernel
+#if NN_QTILE_FASTEST
+    const uint32_t qtiles = gridDim.x / a.splits;
+    const uint32_t qtile = blockIdx.x % qtiles;
+    const uint32_t split = blockIdx.x / qtiles;
+#else
     const uint32_t split = blockIdx.x % a.splits;
     const uint32_t qtile = blockIdx.x / a.splits;
+#endif
     const uint32_t ng = a.ng, np = a.np;
     // lanes beyond NG*NP shadow the last phase of group 0 (same addresses: broadcast) and publish nothing
     const bool live = (uint32_t)tid < ng * np;

@@ -8,18 +8,19 @@ evidence under profiles/: <tag>_ncu_summary.txt (side-by-side metrics + stall re
 import csv, json, os, shutil, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-caps = ["cfg1_qreg", "cfg2_qreg", "cfg3_rtma", "cfg4s_qreg", "cfg5s_qreg", "m1_rreg", "repack_k16"]
-paths = [os.path.join(ROOT, "gpurun_out", f"{tag}_{c}.ncu-rep") for c in caps]
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+caps = ["cfg1_qreg", "cfg2_qreg", "cfg3_rtma", "cfg4_qreg", "cfg5_qreg", "cfg4s_qreg", "cfg5s_qreg", "m100k8_qflex", "m100k3_qflex",
+        "cfg3shard_rtma", "m1_rreg", "repack_k16"]
+paths = [os.path.join(ROOT, "gpurun_out", f"{tag}_{c}.raw.csv") for c in caps]
 paths = [p for p in paths if os.path.exists(p)]
 out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py")] + paths, capture_output=True, text=True).stdout
 hdr = (f"# ncu --set full --clock-control none captures ({tag}), one launch each, nn_bench command lines in scripts/gpu_profile.sh\n"
-       "# cfg4s / cfg5s are 1/16-size slices of configs 4 / 5 (same kernels and tile shapes; the full sizes replay for minutes under ncu)\n")
+       "# all five BASELINE configs at FULL size, through the one-launch search (nn_b200_search_device); m100* = 100 queries x 2^22 references (phased kernel)\n")
 open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.txt"), "w").write(hdr + out)
 print(out)
 
 def raw(path):
-    o = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    o = open(path).read()
     rows = list(csv.reader(o.splitlines()))
     return {h: (v, u) for h, u, v in zip(rows[0], rows[1], rows[2])}
 
@@ -29,8 +30,9 @@ def to_bytes(v, u):
 
 traffic = {}
 for wl, cap, kern, alg in [("cfg1", "cfg1_qreg", "nn_qreg_kernel", 65536 * 3 * 4), ("cfg2", "cfg2_qreg", "nn_qreg_kernel", (1 << 20) * 16 * 4),
-                           ("cfg3", "cfg3_rtma", "nn_rtma_kernel", (1 << 26) * 8 * 4)]:
-    p = os.path.join(ROOT, "gpurun_out", f"{tag}_{cap}.ncu-rep")
+                           ("cfg3", "cfg3_rtma", "nn_rtma_kernel", (1 << 26) * 8 * 4), ("cfg4", "cfg4_qreg", "nn_qreg_kernel", (1 << 24) * 16 * 4),
+                           ]:
+    p = os.path.join(ROOT, "gpurun_out", f"{tag}_{cap}.raw.csv")
     if not os.path.exists(p):
         continue
     d = raw(p)
@@ -38,7 +40,8 @@ for wl, cap, kern, alg in [("cfg1", "cfg1_qreg", "nn_qreg_kernel", 65536 * 3 * 4
                    "algorithmic_bytes": alg, "gpu_time_us": float(d["gpu__time_duration.sum"][0].replace(",", "")) * (1e-3 if d["gpu__time_duration.sum"][1] == "ns" else 1.0 if d["gpu__time_duration.sum"][1] == "us" else 1e3),
                    "source": f"profiles/{tag}_ncu_summary.txt ({tag}_{cap}.ncu-rep, ncu --set full, one launch)"}
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
-src = os.path.join(ROOT, "gpurun_out", f"{tag}_launches_bench_cfg2.csv")
-if os.path.exists(src):
-    shutil.copy(src, os.path.join(ROOT, "profiles", f"{tag}_launches_bench_cfg2.csv"))
+for name in (f"{tag}_launches_bench_cfg4.csv", f"{tag}_launches_bench_cfg2.csv"):
+    src = os.path.join(ROOT, "gpurun_out", name)
+    if os.path.exists(src):
+        shutil.copy(src, os.path.join(ROOT, "profiles", name))
 print(json.dumps(traffic, indent=1))

@@ -14,12 +14,15 @@ WANT = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'smsp__issue_active
         'l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum', 'sm__inst_executed.sum']
 cols = {}
 for path in sys.argv[1:]:
-    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if path.endswith('.csv'):   # already exported on the GPU box (ncu -i X.ncu-rep --page raw --csv)
+        out = open(path).read()
+    else:
+        out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
     cols[path] = d
-print(f"{'metric':64s}", *[f"{p.split('/')[-1].replace('.ncu-rep','')[:21]:>22s}" for p in sys.argv[1:]])
+print(f"{'metric':64s}", *[f"{p.split('/')[-1].replace('.ncu-rep','').replace('.raw.csv','')[:21]:>22s}" for p in sys.argv[1:]])
 keys = [k for k in WANT if any(k in d for d in cols.values())]
 stall = sorted({h for d in cols.values() for h in d if 'issue_stalled' in h and h.endswith('per_issue_active.ratio')})
 for k in keys + stall:

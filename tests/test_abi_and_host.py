@@ -219,3 +219,20 @@ def test_gpu_count_planner(nn):
         g = P(8, 64, n, 8)
         assert g >= last
         last = g
+
+
+def test_peer_merge_needs_a_gpu_and_checks_its_arguments(nn):
+    """nn_b200_peer_*: argument validation works everywhere; without a CUDA device creation fails loudly
+    (there is no host-memory stand-in for the NVLink merge)."""
+    import ctypes
+    import torch
+    L = nn.lib()
+    h = ctypes.c_void_p()
+    assert L.nn_b200_peer_create(10, 2, 2, ctypes.byref(h)) == -1        # rank outside the world
+    assert L.nn_b200_peer_create(-1, 0, 1, ctypes.byref(h)) == -1
+    assert L.nn_b200_peer_search(None, 3, 1, 1, None, None, 0, None, None) == -1
+    if not torch.cuda.is_available():
+        assert L.nn_b200_peer_create(10, 0, 1, ctypes.byref(h)) in (-2, -4)
+        from multicore_hw2_b200 import sharded
+        with pytest.raises(nn.NNError):
+            sharded.PeerMerge(10)
