@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -75,7 +76,7 @@ struct Options
     std::atomic<int64_t> h2d_chunk_bytes{16 << 20};
     std::atomic<int64_t> waves{8};           // qreg: most CTA waves considered
     std::atomic<int64_t> stage_threads{-1};  // pageable inputs: host threads staging into pinned buffers (-1 auto, 0 off)
-    std::atomic<int64_t> stage_min_bytes{4 << 20}; // pageable reference sets from this size on go through the staging threads
+    std::atomic<int64_t> stage_min_bytes{48 << 20}; // pageable reference sets from this size on go through the staging threads
     std::atomic<int64_t> index_graph{1};     // resident index on one GPU: replay a captured CUDA graph for small batches
     std::atomic<int64_t> p2p_merge{1};       // multi-GPU host entry: 1 fold into GPU 0's keys over NVLink, 0 NCCL all-reduce
     std::atomic<int64_t> auto_gpus{1};       // host entry without an explicit GPU count: 1 = plan_gpus decides, 0 = all visible
@@ -1612,6 +1613,20 @@ int ensure_staging(DevCtx &c, int feeders, size_t chunk_bytes)
 
 // `keys0`: non-null = fold into that (peer) key array, already initialised, once `keys_ready` has
 // fired; null = this device's own key array, initialised here.
+// NN_B200_TRACE=1: phase times of the staged ingest on stderr (diagnostics only)
+static bool trace_on()
+{
+    static const bool on = [] {
+        const char *e = getenv("NN_B200_TRACE");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+static double now_us()
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // `lone`: this device is the only one of the call (nothing to merge with).
 int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float *R, int64_t begin, int64_t count,
                    unsigned long long *keys0, cudaEvent_t keys_ready, bool lone)
@@ -1619,12 +1634,15 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
     const size_t bytesS = (size_t)m * k * sizeof(float);
     const size_t bytesR = (size_t)count * k * sizeof(float);
     // Pageable source (what the reference's harness passes): a cudaMemcpyAsync from it is staged by
-    // the driver on one thread at ~11 GB/s.  From 4 MiB on, `feeders` host threads instead copy
+    // the driver on one thread at ~11 GB/s.  From 48 MiB on, `feeders` host threads instead copy
     // alternate 4 MiB chunks into their own pinned double buffers and push them on their own
     // streams, so host copy, DMA and the search of earlier chunks all overlap.  Measured on the B200
     // box (16 cores), 2 GiB reference set: 193 ms (driver) -> 44 ms with 8 threads; pinned: 39 ms.
-    // Threshold: 4 MiB.  (Round 1 staged from 128 MiB on; BASELINE config 2's 64 MiB of malloc'ed
-    // references then took the driver path, ~6 ms -- as long as its search -- against 1.3 ms pinned.)
+    // Threshold: 48 MiB (round 1: 128 MiB).  Measured on the B200 box, one GPU, ms per call, staged / driver
+    // path / pinned: 4 MiB 1.03 / 0.35 / 0.33; 16 MiB 2.0 / 1.6 / 0.72; 32 MiB 3.0 / 2.2 / 1.2;
+    // 64 MiB (BASELINE config 2) 6.7 / 7.0 / 6.2; 256 MiB 7.4 / 23.7 / 5.4.  Below ~48 MiB the driver's
+    // own staging wins: a staged call carries ~1 ms that NN_B200_TRACE=1 shows is spent on the device
+    // after everything has been enqueued (open item), and the chunks cost extra launches.
     int64_t want_feeders = g_opt.stage_threads.load();
     if (want_feeders < 0)
         want_feeders = bytesR >= (size_t)g_opt.stage_min_bytes.load()
@@ -1687,6 +1705,7 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
     std::vector<char> recorded(nchunks, 0);
     int frc = NN_B200_OK;
     std::string ferr;
+    const double t_enq = now_us();
     TaskGroup fgroup; // declared after everything the staging tasks touch: its destructor waits for them
     if (feeders > 0)
     {
@@ -1706,6 +1725,7 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
                         r = 1;
                     fcv.notify_all();
                 };
+                const double t_start = now_us();
                 cudaError_t e = cudaSetDevice(dev);
                 if (e != cudaSuccess)
                     return bail(e, 0);
@@ -1717,12 +1737,17 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
                     const size_t bytes = (size_t)cnt * k * sizeof(float);
                     if (use >= 2 && (e = cudaEventSynchronize(c.stage_ev[t][b])) != cudaSuccess)
                         return bail(e, ci);
+                    const double t_m0 = now_us();
                     memcpy(c.stage[t][b], R + (size_t)(begin + off) * k, bytes);
+                    const double t_m1 = now_us();
                     if ((e = cudaMemcpyAsync(c.dR + (size_t)off * k, c.stage[t][b], bytes, cudaMemcpyHostToDevice,
                                              c.fstream[t])) != cudaSuccess ||
                         (e = cudaEventRecord(c.events[ci + 1], c.fstream[t])) != cudaSuccess ||
                         (e = cudaEventRecord(c.stage_ev[t][b], c.fstream[t])) != cudaSuccess)
                         return bail(e, ci);
+                    if (trace_on())
+                        fprintf(stderr, "[nn_b200] feeder %d chunk %zu: start +%.0f us, memcpy %zu KiB %.0f us, api %.0f us\n", t, ci,
+                                t_start - t_enq, bytes >> 10, t_m1 - t_m0, now_us() - t_m1);
                     {
                         std::lock_guard<std::mutex> lk(fmu);
                         recorded[ci] = 1;
@@ -1748,6 +1773,8 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
                                cudaMemcpyHostToDevice, c.copy));
             CU(cudaEventRecord(c.events[ci + 1], c.copy));
         }
+        if (trace_on() && feeders > 0)
+            fprintf(stderr, "[nn_b200] main: chunk %zu ready at +%.0f us\n", ci, now_us() - t_enq);
         CU(cudaStreamWaitEvent(c.compute, c.events[ci + 1], 0));
         if (lone && nchunks == 1)
         { // the whole search in one launch: its last CTAs store dOut and restore the workspace
@@ -1852,6 +1879,7 @@ template <class Enqueue>
 static int run_sharded_body(int m, int gpus, Enqueue enqueue, int *results, int prev_dev)
 {
     int rc = NN_B200_OK;
+    const double t_call = now_us();
 
     // Merge of the per-GPU candidates.  Default: every GPU's search kernels fold straight into GPU 0's
     // key array with system-scope 64-bit atomicMin over NVLink (the exchange step happens inside the
@@ -1901,6 +1929,8 @@ static int run_sharded_body(int m, int gpus, Enqueue enqueue, int *results, int 
             t_err = errs[g];
             return rcs[g];
         }
+    if (trace_on())
+        fprintf(stderr, "[nn_b200] call: everything enqueued at +%.0f us\n", now_us() - t_call);
 
     if (p2p)
     {
@@ -1952,6 +1982,8 @@ static int run_sharded_body(int m, int gpus, Enqueue enqueue, int *results, int 
         g_ctx.devs[g].ws_dirty = false;
     }
     memcpy(results, c0.hOut, (size_t)m * sizeof(int));
+    if (trace_on())
+        fprintf(stderr, "[nn_b200] call: synchronised at +%.0f us\n", now_us() - t_call);
     (void)prev_dev;
     return NN_B200_OK;
 }
