@@ -9,11 +9,14 @@ Workload (config.workload): BASELINE configs[3] = k=16, m=65,536 queries, n=16,7
 the configuration `north_star` quotes the 1/2/4/8-GPU metric on; it fits one GPU (1 GiB of
 references).  With N GPUs the ONE reference set is sharded over the ranks (strong scaling, v8's job:
 /root/reference/sources/src/core.cu:875-883) and the per-query packed keys are merged with one
-all-reduce(min, u64) over NCCL.  --workload cfg1..cfg5 / --scaling weak select other runs.
+u64-min exchange (NVLink peer atomics or NCCL all-reduce, see --merge).  --workload cfg1..cfg5 /
+--scaling weak select other runs.
 
 One "step" = one complete search with inputs resident in HBM:
   N = 1: ONE kernel launch (nn_b200_search_device: distance + argmin + merge + index store);
-  N > 1: search (packed keys out) -> all-reduce(min) -> keys_unpack.
+  N > 1: one launch per rank with the exchange fused into the search kernels over NVLink peer memory
+         (nn_b200_peer_search) where the merge is latency-bound, else search (packed keys out) ->
+         all-reduce(min) -> keys_unpack (--merge auto|peer|nccl; the other one is timed beside it).
 
 `value`   : pairs/s (m * n_total / step time), CUDA events per step on the launching stream, summed over
             the K steps, max over ranks; L2 flushed between steps.
@@ -513,9 +516,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-all-configs", action="store_true")
-    ap.add_argument("--merge", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--merge", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: peer = the exchange fused into the search kernels over NVLink peer memory (CUDA IPC, "
-                         "system-scope atomicMin into rank 0's keys); nccl = search -> all-reduce(min) -> unpack")
+                         "system-scope atomicMin into rank 0's keys); nccl = search -> all-reduce(min) -> unpack; "
+                         "auto = peer for latency-bound merges (m <= 16384 and >= 40 us of search per rank), else nccl")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="strong (contract default): the workload's ONE reference set is sharded over the ranks "
                          "(v8, core.cu:875-883); weak: every rank owns the workload's n references")
@@ -561,6 +565,14 @@ def main():
     # delayed launches enough to show up as all-reduce skew
     sampler = ClockSampler(local if rank == 0 else -1)
     merge, peer, peer_note = args.merge, None, None
+    if merge == "auto":
+        # Measured on 8 B200s (profiles/README.md): the peer merge pushes one remote atomic per query and rank and
+        # rank 0's last CTA unpacks all m keys, so from ~16K queries on the bandwidth-optimal all-reduce wins
+        # (config 5, m = 2^20: 35.7 vs 33.6 ms; config 4, m = 65536: 185.17 vs 184.94 ms); and when a rank's search
+        # is only a few microseconds (config 1 on 8 GPUs: 12 us) the ranks that are not rank 0 run ahead and spend
+        # the difference waiting inside their kernels (81 vs 55 us per step by the max-over-ranks clock).
+        est_us = 3.0 * k * m * (n_total / world) / (0.85 * sms * 128 * peaks["sm_max_mhz"] * 1e6) * 1e6
+        merge = "peer" if (m <= 16384 and est_us >= 40.0) else "nccl"
     if world > 1 and merge == "peer":
         try:
             from multicore_hw2_b200 import sharded
@@ -575,6 +587,25 @@ def main():
                      merge=merge, peer=peer)
     clocks = sampler.stop()
     nccl_leg = None
+    peer_leg = None
+    if world > 1 and merge == "nccl" and args.merge == "auto":
+        # the other merge beside it (short)
+        try:
+            from multicore_hw2_b200 import sharded
+            pm2 = sharded.PeerMerge(m, group=host_group)
+            lg2 = device_leg(nn, k, m, n_total, max(3, min(args.steps, 10)), 3, dev, world, rank, args.scaling, merge="peer",
+                             peer=pm2)
+            t2 = torch.tensor([sum(lg2["step_ms"]) / len(lg2["step_ms"])], dtype=torch.float64, device=dev)
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            same = torch.tensor([1 if (rank != 0 or torch.equal(lg2["out"], leg["out"])) else 0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            peer_leg = {"ms_per_step": float(t2.item()), "steps": len(lg2["step_ms"]),
+                        "same_result_as_nccl_merge": bool(int(same.item())), "timed_out": pm2.error(),
+                        "step": "one launch per rank: nn_b200_peer_search (merge inside the kernels over NVLink peer memory)"}
+            del lg2
+            pm2.close()
+        except Exception as e:
+            peer_leg = {"unavailable": str(e)[:200]}
     if world > 1 and merge == "peer":
         # the same steps with the exchange as a collective, for comparison (fewer steps)
         lg2 = device_leg(nn, k, m, n_total, max(3, min(args.steps, 10)), 3, dev, world, rank, args.scaling, merge="nccl")
@@ -706,7 +737,7 @@ def main():
             "parity_spot_check": (all(parity.values()) if parity else None),
             "parity_detail": ({"oracle_queries": parity_n, "oracle": "oracle/nn_oracle.c v0 restatement, full reference set",
                                **parity} if parity else None),
-            "all_configs": all_cfg, "nccl_merge": nccl_leg,
+            "all_configs": all_cfg, "nccl_merge": nccl_leg, "peer_merge": peer_leg,
             "clocks": clocks, "wall_ms_per_step_incl_flush": 1e3 * wall_s / args.steps,
             "step_ms_min_max": [min(step_ms), max(step_ms)], "step_ms": [round(x, 4) for x in step_ms[:32]],
             "merge_ms": sum(merge_ms) / len(merge_ms),

@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Fills profiles/README.md.tmpl (round-2 tables) from the committed measurement files under profiles/."""
+import glob
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+
+
+def line(path):
+    txt = open(path).read().strip().splitlines()
+    return json.loads([l for l in txt if l.startswith("{")][-1])
+
+
+t = open(os.path.join(P, "README.md.tmpl")).read()
+b = line(os.path.join(P, "r02_bench_n1.json"))
+ac = b["all_configs"]
+rows = {"1": ac["cfg1"], "2": ac["cfg2"], "3": ac["cfg3"], "5": ac["cfg5"]}
+for c, v in rows.items():
+    t = t.replace(f"@C{c}MS@", f"{v['ms_per_step']:.4f}").replace(f"@C{c}V@", f"{v['value']:.3g}")
+    t = t.replace(f"@C{c}F@", f"{v['roofline']['frac']:.3f}").replace(f"@C{c}E@", f"{v['e2e']['ms_per_call']:.3f}")
+t = t.replace("@C4MS@", f"{b['ms_per_step']:.1f}").replace("@C4V@", f"{b['value']:.3g}").replace("@C4F@", f"**{b['roofline']['frac']:.3f}**")
+t = t.replace("@C4E@", f"{b['e2e']['ms_per_call']:.1f}").replace("@C4P@", f"{b['e2e']['pinned']['ms_per_call']:.1f}")
+t = t.replace("@C4I@", f"{b['e2e']['resident_index']['ms_per_call']:.1f}")
+cb = b["cpu_baseline"]
+t = t.replace("@CPUC@", str(cb["cores"])).replace("@CPUV@", f"{cb['value']:.3g}").replace("@CPU1@", f"{cb.get('value_1_thread', 0):.3g}")
+rg = ac.get("reference_gpu_on_this_b200", {})
+if "samples" in rg:
+    ours = {6: ac["cfg1"]["e2e"]["ms_per_call"]}
+    txt = "; ".join(f"TA sample {s['sample']} ({s['k']}, {s['m']}, {s['n']}): {s['ms_med']:.3f} ms (best {s['ms_best']:.3f}), "
+                    f"{s['mismatches_vs_v0']} index mismatches vs v0" for s in rg["samples"])
+    txt += f". This library, same call: config 1 = TA sample 6 {ours[6]:.3f} ms (**{rg['samples'][0]['ms_med'] / ours[6]:.1f}×**)."
+else:
+    txt = str(rg)
+t = t.replace("@REFGPU@", txt)
+
+# few-query band
+cr = json.load(open(os.path.join(P, "r02_fewquery_crossover.json")))["rows"]
+r1 = {(3, 100): "169 (0.60)", (8, 100): "411 (0.66)", (16, 100): "791 (0.68)", (3, 32): "79", (8, 32): "140", (16, 32): "260",
+      (3, 8): "26", (8, 8): "42", (16, 8): "73"}
+out = []
+for r in cr:
+    if r["n"] != 1 << 22 or r["m"] not in (8, 16, 32, 64, 100, 128, 200):
+        continue
+    bound = 3 * r["k"] * r["m"] * r["n"] / 37.22496e12 * 1e6
+    def f(key):
+        return f"{r[key]:.0f} ({bound / r[key]:.2f})" if key in r else "—"
+    out.append(f"| ({r['k']}, {r['m']}) | {f('qreg_us')} | {f('rtma_us')} | {f('qflex_us')} | {r['auto_plan']} | {r1.get((r['k'], r['m']), '')} |")
+t = t.replace("@CROSS@", "\n".join(out))
+
+gc = json.load(open(os.path.join(P, "r02_gpu_count.json")))
+vis = gc["visible"]
+cols = [str(g) for g in (1, 2, 4, 8) if g <= vis]
+hdr = "| shape (k, m, n) | " + " | ".join(f"{g} GPU{'s' if g != '1' else ''}" for g in cols) + " | planned | best | with the planner in charge (GPUs used) |"
+sep = "|" + "---|" * (len(cols) + 4)
+out = [hdr, sep]
+for r in gc["rows"]:
+    out.append(f"| {r['name']} ({r['k']}, {r['m']}, {r['n']}) | " + " | ".join(f"{r['ms'][g]:.3f}" for g in cols) +
+               f" | {r['planned']} | {r['best']} | {r['ms_auto']:.3f} ({r['auto_used']}) |")
+t = t.replace("| shape (k, m, n) | 1 GPU | 2 GPUs | 4 GPUs | planned | best | with the planner in charge (GPUs used) |\n|---|---|---|---|---|---|---|\n@GPUCOUNT@", "\n".join(out))
+t = t.replace("ms per call on 1 / 2 / 4 GPUs", "ms per call on " + " / ".join(cols) + " GPUs").replace("on 4 GPUs)", f"on {vis} GPUs)")
+
+# multi-GPU
+mg = []
+for path in sorted(glob.glob(os.path.join(P, "r02_bench_n*_cfg*.json"))):
+    try:
+        d = line(path)
+    except Exception:
+        continue
+    name = os.path.basename(path).replace("r02_bench_", "").replace(".json", "")
+    n = d.get("nccl_merge") or {}
+    mg.append((name, d, n))
+base = {"cfg4": b["ms_per_step"]}
+for c in ("cfg1", "cfg2", "cfg3", "cfg5"):
+    base[c] = ac[c]["ms_per_step"]
+rowsm = ["| run | GPUs | merge | ms per step | parallel efficiency vs 1 GPU | per-rank kernel ms (min / max) | same steps with the NCCL all-reduce | oracle check |", "|---|---|---|---|---|---|---|---|"]
+for name, d, n in mg:
+    N = d["n_gpus"]
+    cfg = name.split("_")[1]
+    eff = base[cfg] / (N * d["ms_per_step"])
+    km = d["kernel_ms_min_max_over_ranks"]
+    rowsm.append(f"| {cfg} | {N} | {d['config']['merge']} | {d['ms_per_step']:.4f} | {eff:.3f} | {km[0]:.4f} / {km[1]:.4f} | "
+                 f"{n.get('ms_per_step', float('nan')):.4f} (kernel {n.get('kernel_ms', float('nan')):.4f} + all-reduce {n.get('merge_ms', float('nan')):.4f} + unpack) | "
+                 f"{d.get('parity_spot_check') if d.get('parity_spot_check') is not None else 'n/a'} |")
+t = t.replace("@MULTI@", "\n".join(rowsm) if mg else "(see the driver's SCALE record)")
+pg = os.path.join(P, "r02_pageable.txt")
+t = t.replace("@PAGEABLE@", open(pg).read() if os.path.exists(pg) else "")
+open(os.path.join(P, "README.md"), "w").write(t)
+print("profiles/README.md written;", len(mg), "multi-GPU lines")
