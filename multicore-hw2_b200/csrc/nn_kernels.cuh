@@ -74,6 +74,9 @@
 #ifndef NN_QREG_PREFETCH
 #define NN_QREG_PREFETCH 1 // query-register kernel: load the next reference group while computing the current one
 #endif
+#ifndef NN_QFLEX_MINB5
+#define NN_QFLEX_MINB5 0 // phased kernel: compile the small-k instantiations for 5 CTAs per SM (A/B)
+#endif
 #ifndef NN_QFLEX_UNROLL_Q8
 #define NN_QFLEX_UNROLL_Q8 1 // phased query-register kernel: chunks unrolled in the tile loop, by queries per thread
 #endif
@@ -891,12 +894,24 @@ __device__ __forceinline__ void qflex_chunk(const float *__restrict__ sm, const 
     }
 }
 
+// CTAs per SM the phased kernel is compiled for: 5 where the thread's queries and two reference groups
+// leave room under 102 registers (small k), else what the query-register kernel uses.
+template <int K, int Q>
+constexpr int qflex_minb()
+{
+    return (NN_QFLEX_MINB5 && Q * K + 2 * Geo<K>::G * K + 52 <= 102) ? 5 : qreg_minb<K, Q, 2>();
+}
+
 template <int K, int Q, int NT>
-__global__ void __launch_bounds__(NT, qreg_minb<K, Q, 2>()) nn_qflex_kernel(const QflexArgs a)
+__global__ void __launch_bounds__(NT, qflex_minb<K, Q>()) nn_qflex_kernel(const QflexArgs a)
 {
     using C = QregCfg<K>;
     constexpr int G = Geo<K>::G, F4 = Geo<K>::F4, CH = C::CH, CHG = CH / G, STAGES = C::STAGES;
-    constexpr int UNR = Q >= 8 ? NN_QFLEX_UNROLL_Q8 : (Q >= 4 ? NN_QFLEX_UNROLL_Q4 : NN_QFLEX_UNROLL_Q2);
+    // (Q = 4: not unrolled for k = 5..8 -- 25-30 fewer registers, k = 5: 0.74 -> 0.80 of the roofline at
+    // m = 100, k = 8: 0.805 -> 0.818; k <= 4 and k >= 9 measured 0.5-1% better with two chunks per trip)
+    constexpr int UNR = Q >= 8 ? NN_QFLEX_UNROLL_Q8
+                               : (Q >= 4 ? ((NN_QFLEX_UNROLL_Q4 == 2 && K >= 5 && K <= 8) ? 1 : NN_QFLEX_UNROLL_Q4)
+                                         : NN_QFLEX_UNROLL_Q2);
     static_assert(CH % 2 == 0 && CH % G == 0, "chunks are whole groups and an even number of points");
     static_assert((size_t)NT * Q * 8 <= (size_t)STAGES * C::TILE_BYTES, "the phase exchange reuses the ring");
     extern __shared__ __align__(128) unsigned char smem_raw[];
