@@ -77,6 +77,8 @@ struct Options
     std::atomic<int64_t> waves{8};           // qreg: most CTA waves considered
     std::atomic<int64_t> stage_threads{-1};  // pageable inputs: host threads staging into pinned buffers (-1 auto, 0 off)
     std::atomic<int64_t> stage_min_bytes{48 << 20}; // pageable reference sets from this size on go through the staging threads
+    std::atomic<int64_t> search_group{8};    // host entry: at most this many landed H2D chunks are searched by one launch
+    std::atomic<int64_t> stage_one_stream{1}; // staging threads push their copies on the shared copy stream (5% faster than a stream each)
     std::atomic<int64_t> index_graph{1};     // resident index on one GPU: replay a captured CUDA graph for small batches
     std::atomic<int64_t> p2p_merge{1};       // multi-GPU host entry: 1 fold into GPU 0's keys over NVLink, 0 NCCL all-reduce
     std::atomic<int64_t> auto_gpus{1};       // host entry without an explicit GPU count: 1 = plan_gpus decides, 0 = all visible
@@ -121,6 +123,10 @@ extern "C" int nn_b200_set_option(const char *name, int64_t value)
         g_opt.stage_threads = value;
     else if (s == "stage_min_bytes")
         g_opt.stage_min_bytes = value;
+    else if (s == "search_group")
+        g_opt.search_group = value;
+    else if (s == "stage_one_stream")
+        g_opt.stage_one_stream = value;
     else
         return fail(NN_B200_EINVAL, "unknown option '%s'", name);
     g_opt_epoch++;
@@ -1706,6 +1712,7 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
     int frc = NN_B200_OK;
     std::string ferr;
     const double t_enq = now_us();
+    const bool one_stream = g_opt.stage_one_stream.load() != 0;
     TaskGroup fgroup; // declared after everything the staging tasks touch: its destructor waits for them
     if (feeders > 0)
     {
@@ -1740,10 +1747,11 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
                     const double t_m0 = now_us();
                     memcpy(c.stage[t][b], R + (size_t)(begin + off) * k, bytes);
                     const double t_m1 = now_us();
-                    if ((e = cudaMemcpyAsync(c.dR + (size_t)off * k, c.stage[t][b], bytes, cudaMemcpyHostToDevice,
-                                             c.fstream[t])) != cudaSuccess ||
-                        (e = cudaEventRecord(c.events[ci + 1], c.fstream[t])) != cudaSuccess ||
-                        (e = cudaEventRecord(c.stage_ev[t][b], c.fstream[t])) != cudaSuccess)
+                    cudaStream_t fs = one_stream ? c.copy : c.fstream[t];
+                    if ((e = cudaMemcpyAsync(c.dR + (size_t)off * k, c.stage[t][b], bytes, cudaMemcpyHostToDevice, fs)) !=
+                            cudaSuccess ||
+                        (e = cudaEventRecord(c.events[ci + 1], fs)) != cudaSuccess ||
+                        (e = cudaEventRecord(c.stage_ev[t][b], fs)) != cudaSuccess)
                         return bail(e, ci);
                     if (trace_on())
                         fprintf(stderr, "[nn_b200] feeder %d chunk %zu: start +%.0f us, memcpy %zu KiB %.0f us, api %.0f us\n", t, ci,
@@ -1757,25 +1765,37 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
             });
     }
 
-    for (size_t ci = 0; ci < nchunks; ++ci)
+    // Copy granularity and search granularity are decoupled: the copies stay small (early start, double
+    // buffers), but once the pipeline runs several landed chunks are searched by ONE launch -- every
+    // launch of a big search has its own wave tail, and config 4's 1 GiB in 4 MiB chunks meant 260
+    // launches (e2e 1538 ms for a 1473 ms search; 16 MiB pinned chunks: 1487 ms).
+    const size_t group_max = (size_t)std::max<int64_t>(1, std::min<int64_t>(g_opt.search_group.load(), (int64_t)nchunks / 24));
+    for (size_t ci = 0; ci < nchunks;)
     {
-        const int64_t off = chunks[ci].first, cnt = chunks[ci].second;
-        if (feeders > 0)
+        const size_t ce = std::min(nchunks, ci + (ci < 4 ? (size_t)1 : group_max));
+        const int64_t off = chunks[ci].first;
+        int64_t cnt = 0;
+        for (size_t cj = ci; cj < ce; ++cj)
         {
-            std::unique_lock<std::mutex> lk(fmu);
-            fcv.wait(lk, [&] { return recorded[ci] != 0; });
-            if (frc != NN_B200_OK)
-                return fail(frc, "%s", ferr.c_str());
+            if (feeders > 0)
+            {
+                std::unique_lock<std::mutex> lk(fmu);
+                fcv.wait(lk, [&] { return recorded[cj] != 0; });
+                if (frc != NN_B200_OK)
+                    return fail(frc, "%s", ferr.c_str());
+            }
+            else
+            {
+                CU(cudaMemcpyAsync(c.dR + (size_t)chunks[cj].first * k, R + (size_t)(begin + chunks[cj].first) * k,
+                                   (size_t)chunks[cj].second * k * sizeof(float), cudaMemcpyHostToDevice, c.copy));
+                CU(cudaEventRecord(c.events[cj + 1], c.copy));
+            }
+            if (trace_on() && feeders > 0)
+                fprintf(stderr, "[nn_b200] main: chunk %zu ready at +%.0f us\n", cj, now_us() - t_enq);
+            CU(cudaStreamWaitEvent(c.compute, c.events[cj + 1], 0));
+            cnt += chunks[cj].second;
         }
-        else
-        {
-            CU(cudaMemcpyAsync(c.dR + (size_t)off * k, R + (size_t)(begin + off) * k, (size_t)cnt * k * sizeof(float),
-                               cudaMemcpyHostToDevice, c.copy));
-            CU(cudaEventRecord(c.events[ci + 1], c.copy));
-        }
-        if (trace_on() && feeders > 0)
-            fprintf(stderr, "[nn_b200] main: chunk %zu ready at +%.0f us\n", ci, now_us() - t_enq);
-        CU(cudaStreamWaitEvent(c.compute, c.events[ci + 1], 0));
+        ci = ce;
         if (lone && nchunks == 1)
         { // the whole search in one launch: its last CTAs store dOut and restore the workspace
             rc = search_device_impl(k, m, cnt, c.dS, c.dR, (uint32_t)begin, c.dWs, c.dOut, nullptr, c.compute);
