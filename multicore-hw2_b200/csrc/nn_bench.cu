@@ -285,6 +285,16 @@ int main(int argc, char **argv)
             c.ldg = atoi(val());
         else if (a == "--quant")
             c.quant = atoi(val());
+        else if (a == "--opt")
+        { // --opt name=value: any nn_b200_set_option knob
+            std::string kv = val();
+            const size_t eq = kv.find('=');
+            if (eq == std::string::npos || nn_b200_set_option(kv.substr(0, eq).c_str(), atoll(kv.c_str() + eq + 1)) != 0)
+            {
+                fprintf(stderr, "bad --opt %s\n", kv.c_str());
+                return 1;
+            }
+        }
         else if (a == "--fused")
             c.fused = atoi(val());
         else if (a == "--tag")

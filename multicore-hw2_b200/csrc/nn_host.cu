@@ -77,6 +77,7 @@ struct Options
     std::atomic<int64_t> waves{8};           // qreg: most CTA waves considered
     std::atomic<int64_t> stage_threads{-1};  // pageable inputs: host threads staging into pinned buffers (-1 auto, 0 off)
     std::atomic<int64_t> stage_min_bytes{48 << 20}; // pageable reference sets from this size on go through the staging threads
+    std::atomic<int64_t> flex_deep_ring{1};  // phased kernel ring: 1 = 4 x ~12 KB (default), 0 = 3 x ~8 KB, -1 = deep only beyond 8 phases
     std::atomic<int64_t> search_group{8};    // host entry: at most this many landed H2D chunks are searched by one launch
     std::atomic<int64_t> stage_one_stream{1}; // staging threads push their copies on the shared copy stream (5% faster than a stream each)
     std::atomic<int64_t> index_graph{1};     // resident index on one GPU: replay a captured CUDA graph for small batches
@@ -125,6 +126,8 @@ extern "C" int nn_b200_set_option(const char *name, int64_t value)
         g_opt.stage_min_bytes = value;
     else if (s == "search_group")
         g_opt.search_group = value;
+    else if (s == "flex_deep_ring")
+        g_opt.flex_deep_ring = value;
     else if (s == "stage_one_stream")
         g_opt.stage_one_stream = value;
     else
@@ -178,13 +181,13 @@ static cudaError_t k_launch_qflex(int k, int q, const QflexArgs &a, uint32_t qti
     }
     return cudaErrorInvalidValue;
 }
-static cudaError_t k_query_qflex(int k, int q, FlexInfo *fi)
+static cudaError_t k_query_qflex(int k, int q, int smem_bytes, FlexInfo *fi)
 {
     switch (k)
     {
 #define X(KK)                                                                                                          \
     case KK:                                                                                                           \
-        return query_qflex<KK>(q, fi);
+        return query_qflex<KK>(q, smem_bytes, fi);
         NN_FOR_K(X)
 #undef X
     }
@@ -346,7 +349,7 @@ struct Plan
     int tile_refs = 0; // rtma
     // qflex (shares q, occ, regs, qtiles, splits, refs_per_split with qreg)
     int ng = 0, np = 0;
-    uint32_t tile_queries = 0, tile_groups = 0;
+    uint32_t tile_queries = 0, tile_groups = 0, stages = 0, stage_floats = 0;
     // qreg
     int q = 0, scalar = 0, tile_q = 0, tile_r = 0, occ = 0, regs = 0;
     uint32_t qtiles = 0, splits = 0, refs_per_split = 0;
@@ -514,6 +517,30 @@ static FlexLayout flex_layout(int k, int64_t m, int forced_q)
     }
     return best;
 }
+// Ring geometry of the phased kernel for a layout: four stages of ~12 KB (48 KB per CTA: four CTAs per
+// SM still fit).  With the query-register kernel's own 3 x ~8 KB a thread of a many-phase layout gets only
+// one or two chunks per tile; the deeper ring measured 1-3% faster at every shape (B200, n = 2^22:
+// k=16, m=25: 220 -> 213 us; k=3, m=64: 92.1 -> 90.1 us), never slower.
+struct FlexRing
+{
+    int stages, stage_floats, tile_groups, smem_bytes;
+};
+static FlexRing flex_ring(int k, const FlexLayout &L, int64_t deep)
+{
+    const FlexGeo fg = flex_geo(k);
+    const int group_floats = fg.g * k, unit = L.np * fg.chg; // groups in one round of all phases
+    FlexRing r;
+    const bool many = deep > 0 || (deep < 0 && L.np > 8);
+    r.stages = many ? 4 : 3;
+    const int cap_groups = many ? std::max(unit, (12 * 1024 / 4) / group_floats) : fg.trg;
+    r.tile_groups = std::max(1, cap_groups / unit) * unit;
+    r.stage_floats = (r.tile_groups * group_floats + 3) / 4 * 4;
+    while (r.stages > 2 && 128 + (int64_t)r.stages * r.stage_floats * 4 > 56 * 1024)
+        --r.stages;
+    r.smem_bytes = 128 + r.stages * r.stage_floats * 4;
+    return r;
+}
+
 // Split count for a phased layout: same candidates and time model as plan_splits, with every thread
 // visiting 1/np of its CTA's references and splits that are whole rounds of np * CH references.
 static double plan_flex_splits(int k, const FlexLayout &L, int occ, int sms, int64_t n, int64_t wmax, int64_t forced,
@@ -613,7 +640,7 @@ static int auto_variant(int k, int m, int64_t n)
         const FlexLayout L = flex_layout(k, m, 0);
         if (L.np >= 2)
         {
-            const double t_flex = 15.0 + 1.07 * L.cost * c * mrefs + 0.6 * (x * 4.0 / 6.5);
+            const double t_flex = 15.0 + 0.3 * L.np + 1.07 * L.cost * c * mrefs + 0.6 * (x * 4.0 / 6.5);
             if (t_flex < t_best)
             {
                 best = 5;
@@ -711,8 +738,9 @@ static int make_plan_uncached(int k, int m, int64_t n, bool soa, const DevInfo &
         if (L.q == 0)
             return fail(NN_B200_EINVAL, "no phased query-register layout for k=%d m=%d (qreg_q=%d)", k, m,
                         (int)g_opt.qreg_q.load());
+        const FlexRing ring = flex_ring(k, L, g_opt.flex_deep_ring.load());
         FlexInfo fi{};
-        cudaError_t e = k_query_qflex(k, L.q, &fi);
+        cudaError_t e = k_query_qflex(k, L.q, ring.smem_bytes, &fi);
         if (e != cudaSuccess)
             return fail(NN_B200_ECUDA, "phased query-register kernel query failed for k=%d q=%d: %s", k, L.q,
                         cudaGetErrorString(e));
@@ -729,7 +757,9 @@ static int make_plan_uncached(int k, int m, int64_t n, bool soa, const DevInfo &
         p->regs = fi.regs;
         p->qtiles = (uint32_t)L.qtiles;
         p->tile_queries = (uint32_t)L.tile_queries;
-        p->tile_groups = (uint32_t)((fg.trg / (L.np * fg.chg)) * (L.np * fg.chg));
+        p->tile_groups = (uint32_t)ring.tile_groups;
+        p->stages = (uint32_t)ring.stages;
+        p->stage_floats = (uint32_t)ring.stage_floats;
         p->splits = (uint32_t)spl;
         p->refs_per_split = (uint32_t)rps;
     }
@@ -924,6 +954,8 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
         a.ng = (uint32_t)p.ng;
         a.np = (uint32_t)p.np;
         a.tile_groups = p.tile_groups;
+        a.stages = p.stages;
+        a.stage_floats = p.stage_floats;
         a.keys = keys;
         a.neg_zero = -0.0f;
         a.peer_keys = peer;
@@ -1036,9 +1068,9 @@ extern "C" int nn_b200_describe_plan(int k, int m, int64_t n, char *buf, size_t 
                  p.refs_per_split, p.qtiles * p.splits, di.sms);
     else if (p.variant == 5)
         snprintf(buf, len,
-                 "qflex k=%d Q=%d groups=%d phases=%d tile=%uq x %ug regs=%d occ=%d qtiles=%u splits=%u refs/split=%u "
+                 "qflex k=%d Q=%d groups=%d phases=%d tile=%uq x %ug ring=%ux%uK regs=%d occ=%d qtiles=%u splits=%u refs/split=%u "
                  "ctas=%u sms=%d",
-                 k, p.q, p.ng, p.np, p.tile_queries, p.tile_groups, p.regs, p.occ, p.qtiles, p.splits, p.refs_per_split,
+                 k, p.q, p.ng, p.np, p.tile_queries, p.tile_groups, p.stages, p.stage_floats * 4 / 1024, p.regs, p.occ, p.qtiles, p.splits, p.refs_per_split,
                  p.qtiles * p.splits, di.sms);
     else if (p.variant == 2)
         snprintf(buf, len, "rreg k=%d f32x2-pairs regs=%d ctas/sm=%d ctas=%d passes8=%d tail=%d sms=%d", k, p.regs,
@@ -1208,7 +1240,7 @@ extern "C" int nn_b200_warmup(void)
         }
         FlexInfo fi{};
         for (int q : {2, 4, 8})
-            if (k_query_qflex(k, q, &fi) != cudaSuccess)
+            if (k_query_qflex(k, q, 32 * 1024, &fi) != cudaSuccess)
                 (void)cudaGetLastError(); // 8 queries per thread: k <= 8 only
     }
     cudaFuncAttributes fa;

@@ -1,10 +1,15 @@
 // nn_kernels.cuh -- sm_100a kernels of the brute-force 1-NN path.
 //
 // What is replaced (all in /root/reference/sources/src/core.cu):
-//   cudaCallbackKernel<1024>   808-855 (v7 copy 662-709)   -> nn_qreg_kernel / nn_rreg_kernel
-//   mat_inv_kernel             792-807                      -> nn_repack_soa_kernel (nn_repack.cu);
-//                                                              the search kernels read AoS directly
-//   host second-level reduce   765-787, 936-957             -> 64-bit atomicMin on packed keys
+//   cudaCallbackKernel<1024>   808-855 (v7 copy 662-709)   -> nn_qreg_kernel (many queries), nn_qflex_kernel
+//                                                              (25 .. a few hundred), nn_rtma_kernel (5..24),
+//                                                              nn_rreg_kernel (1..4)
+//   mat_inv_kernel             792-807                      -> nn_repack_soa_kernel; the search kernels read
+//                                                              AoS directly
+//   host second-level reduce   765-787, 936-957             -> 64-bit atomicMin on packed keys; finish_group:
+//                                                              the last CTA per query tile stores the indices
+//                                                              (one launch per search); peer_push_group: the
+//                                                              same across processes over NVLink peer memory
 //
 // Arithmetic contract (v0, core.cu:44-54): d2 = ((d0*d0 + d1*d1) + d2*d2) + ... with
 // d_i = q_i - r_i, every operation IEEE round-to-nearest, never fused.  The packed
@@ -835,6 +840,10 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
 // The phases of a query meet in shared memory at the end (the ring is reused as a [Q][128] key
 // array), so a CTA still issues one atomicMin per query.
 // =============================================================================================
+constexpr int kFlexMaxStages = 8;
+constexpr int kFlexRingOffset = 128; // barriers first (a fixed place whatever the ring), then the ring
+constexpr int kFlexMaxSmem = 56 * 1024; // per CTA: four CTAs per SM stay resident
+
 template <int K, int Q>
 __device__ __forceinline__ void qflex_chunk(const float *__restrict__ sm, const uint32_t gstride,
                                             const float (&q)[Q][K], float (&cm)[Q], const float2 nz,
@@ -906,17 +915,20 @@ template <int K, int Q, int NT>
 __global__ void __launch_bounds__(NT, qflex_minb<K, Q>()) nn_qflex_kernel(const QflexArgs a)
 {
     using C = QregCfg<K>;
-    constexpr int G = Geo<K>::G, F4 = Geo<K>::F4, CH = C::CH, CHG = CH / G, STAGES = C::STAGES;
+    constexpr int G = Geo<K>::G, F4 = Geo<K>::F4, CH = C::CH, CHG = CH / G;
+    // The ring geometry is a launch parameter: layouts with many phases give every thread only one or two
+    // chunks per 8 KB tile, so the per-tile barrier and the TMA latency (two tiles in flight) showed
+    // (time = compute + ~0.6 x HBM time); they get more and larger stages (host: flex_ring).
+    const uint32_t STAGES = a.stages;
     // (Q = 4: not unrolled for k = 5..8 -- 25-30 fewer registers, k = 5: 0.74 -> 0.80 of the roofline at
     // m = 100, k = 8: 0.805 -> 0.818; k <= 4 and k >= 9 measured 0.5-1% better with two chunks per trip)
     constexpr int UNR = Q >= 8 ? NN_QFLEX_UNROLL_Q8
                                : (Q >= 4 ? ((NN_QFLEX_UNROLL_Q4 == 2 && K >= 5 && K <= 8) ? 1 : NN_QFLEX_UNROLL_Q4)
                                          : NN_QFLEX_UNROLL_Q2);
     static_assert(CH % 2 == 0 && CH % G == 0, "chunks are whole groups and an even number of points");
-    static_assert((size_t)NT * Q * 8 <= (size_t)STAGES * C::TILE_BYTES, "the phase exchange reuses the ring");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *tiles = reinterpret_cast<float *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);         // up to kFlexMaxStages barriers
+    float *tiles = reinterpret_cast<float *>(smem_raw + kFlexRingOffset); // stages x stage_floats (>= NT*Q*8 bytes in all)
 
     const int tid = threadIdx.x;
     // CTA order: see nn_qreg_kernel
@@ -953,17 +965,15 @@ __global__ void __launch_bounds__(NT, qflex_minb<K, Q>()) nn_qflex_kernel(const 
         const uint32_t first = r0 + t * tile_refs;
         const uint32_t bytes = min(tile_refs, r1c - first) * (uint32_t)(K * 4);
         mbar_expect_tx(&full[stage], bytes);
-        bulk_g2s(tiles + (size_t)stage * C::TILE_FLOATS, a.R + (size_t)first * K, bytes, &full[stage]);
+        bulk_g2s(tiles + (size_t)stage * a.stage_floats, a.R + (size_t)first * K, bytes, &full[stage]);
     };
     if (tid == 0)
     {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s)
+        for (uint32_t s = 0; s < STAGES; ++s)
             mbar_init(&full[s], 1);
         mbar_fence_init();
-#pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s)
-            if ((uint32_t)s < ntiles)
+        for (uint32_t s = 0; s + 1 < STAGES; ++s)
+            if (s < ntiles)
                 issue(s, s);
     }
 
@@ -994,7 +1004,7 @@ __global__ void __launch_bounds__(NT, qflex_minb<K, Q>()) nn_qflex_kernel(const 
         mbar_wait(&full[stage], parity);
         const uint32_t ref0 = r0 + t * tile_refs;
         const uint32_t nch = min(tile_refs, r1c - ref0) / round; // chunks per thread in this tile
-        const float *sm = tiles + (size_t)stage * C::TILE_FLOATS + (size_t)p * (G * K);
+        const float *sm = tiles + (size_t)stage * a.stage_floats + (size_t)p * (G * K);
         float4 nxt[F4];
 #pragma unroll
         for (int i = 0; i < F4; ++i)
@@ -1051,7 +1061,7 @@ __global__ void __launch_bounds__(NT, qflex_minb<K, Q>()) nn_qflex_kernel(const 
     // with v0's arithmetic.  (Every thread resolving its own Q candidates first cost Q dependent L2
     // round trips per thread -- 8 at Q = 8 -- for candidates of which all but one per query lose.)
     __syncthreads();
-    float *xb = reinterpret_cast<float *>(smem_raw);
+    float *xb = tiles;
     uint32_t *xr = reinterpret_cast<uint32_t *>(xb + Q * NT);
 #pragma unroll
     for (int j = 0; j < Q; ++j)

@@ -137,19 +137,23 @@ static cudaError_t launch_qflex_one(const QflexArgs &a, uint32_t qtiles, cudaStr
     auto kern = nn_qflex_kernel<K, Q, 128>;
     static PerDeviceOnce once;
     const cudaError_t e = once([&] {
-        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QregCfg<K>::SMEM);
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlexMaxSmem);
     });
     if (e != cudaSuccess)
         return e;
-    kern<<<qtiles * a.splits, 128, QregCfg<K>::SMEM, st>>>(a);
+    const size_t smem = (size_t)kFlexRingOffset + (size_t)a.stages * a.stage_floats * 4;
+    if (a.stages < 2 || a.stages > (uint32_t)kFlexMaxStages || smem > (size_t)kFlexMaxSmem ||
+        (size_t)a.stages * a.stage_floats * 4 < (size_t)128 * Q * 8 || (size_t)a.tile_groups * Geo<K>::G * K > a.stage_floats)
+        return cudaErrorInvalidValue;
+    kern<<<qtiles * a.splits, 128, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 template <int K, int Q>
-static cudaError_t query_qflex_one(FlexInfo *info)
+static cudaError_t query_qflex_one(int smem_bytes, FlexInfo *info)
 {
     auto kern = nn_qflex_kernel<K, Q, 128>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QregCfg<K>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlexMaxSmem);
     if (e != cudaSuccess)
         return e;
     cudaFuncAttributes fa;
@@ -157,11 +161,11 @@ static cudaError_t query_qflex_one(FlexInfo *info)
     if (e != cudaSuccess)
         return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, QregCfg<K>::SMEM);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, (size_t)smem_bytes);
     if (e != cudaSuccess)
         return e;
     info->regs = fa.numRegs;
-    info->smem = (int)QregCfg<K>::SMEM;
+    info->smem = smem_bytes;
     info->occ = occ;
     info->ch = QregCfg<K>::CH;
     info->g = Geo<K>::G;
@@ -195,9 +199,9 @@ cudaError_t launch_qflex<NN_K>(int q, const QflexArgs &a, uint32_t qtiles, cudaS
 }
 
 template <>
-cudaError_t query_qflex<NN_K>(int q, FlexInfo *info)
+cudaError_t query_qflex<NN_K>(int q, int smem_bytes, FlexInfo *info)
 {
-    return qflex_dispatch(q, [&](auto qc) { return query_qflex_one<NN_K, decltype(qc)::value>(info); });
+    return qflex_dispatch(q, [&](auto qc) { return query_qflex_one<NN_K, decltype(qc)::value>(smem_bytes, info); });
 }
 
 // ---- reference-register kernel ------------------------------------------------------------------

@@ -77,7 +77,9 @@ struct QflexArgs
     uint32_t refs_per_split; // multiple of np * CH references (the last split takes what is left)
     uint32_t tile_queries;   // queries per query tile, <= ng * Q
     uint32_t ng, np;         // ng * np <= 128
-    uint32_t tile_groups;    // reference groups per ring stage: a multiple of np * CH / G, <= TR / G
+    uint32_t tile_groups;    // reference groups per ring stage: a multiple of np * CH / G that fits a stage
+    uint32_t stages;         // ring depth (2..8)
+    uint32_t stage_floats;   // floats per ring stage (a multiple of 4; dynamic smem = 128 + stages * stage_floats * 4)
     unsigned long long *keys;
     float neg_zero;
     int peer_keys;
@@ -119,7 +121,7 @@ struct FlexInfo
 template <int K>
 cudaError_t launch_qflex(int q, const QflexArgs &a, uint32_t qtiles, cudaStream_t st);
 template <int K>
-cudaError_t query_qflex(int q, FlexInfo *info);
+cudaError_t query_qflex(int q, int smem_bytes, FlexInfo *info); // occupancy for that much dynamic shared memory
 template <int K>
 cudaError_t launch_rreg(int mq, bool soa, const RregArgs &a, dim3 grid, cudaStream_t st);
 template <int K>
