@@ -429,6 +429,35 @@ int main(int argc, char **argv)
                     add("qflex", k, m, n, 5, 0, 2, 8, 0);
                 }
     }
+    else if (sweep == "fuzz")
+    {
+        // random shapes, planner in charge, every result against the plain kernel: odd sizes, every k, query
+        // counts on both sides of every family boundary, tie-heavy and plain data, one-launch and building-block paths
+        uint64_t z = 0x243F6A8885A308D3ull;
+        auto rnd = [&](uint64_t lim) {
+            z ^= z << 13;
+            z ^= z >> 7;
+            z ^= z << 17;
+            return (long long)(z % lim);
+        };
+        for (int i = 0; i < 240; ++i)
+        {
+            Cfg x;
+            x.tag = "fuzz";
+            x.k = 3 + (int)rnd(14);
+            const int cls = (int)rnd(6);
+            x.m = cls == 0 ? 1 + (int)rnd(8) : (cls == 1 ? 5 + (int)rnd(30) : (cls == 2 ? 20 + (int)rnd(120) : (cls == 3 ? 100 + (int)rnd(500) : 1 + (int)rnd(3000))));
+            const int ncls = (int)rnd(5);
+            x.n = ncls == 0 ? 1 + rnd(40) : (ncls == 1 ? 1 + rnd(3000) : (ncls == 2 ? 1000 + rnd(60000) : 20000 + rnd(400000)));
+            x.variant = 0;
+            x.check = 1;
+            x.quant = (i % 3 == 0) ? 8 : 0;
+            x.fused = i % 2;
+            x.iters = 1;
+            x.warmup = 0;
+            list.push_back(x);
+        }
+    }
     else if (sweep == "check")
     {
         // correctness against the plain kernel on tie-heavy data, all k, awkward sizes

@@ -196,6 +196,22 @@ def test_nn_bench_cross_check_sweep(nn):
         [(r["k"], r["m"], r["plan"][:20]) for r in rows if r["mismatch_vs_plain"] != 0]
 
 
+def test_nn_bench_fuzz_sweep(nn):
+    """`nn_bench --sweep fuzz`: 240 pseudo-random shapes (every k, query counts on both sides of every
+    kernel-family boundary, reference counts from 1 to 420k, a third on an 8-level grid) with the
+    planner in charge, alternating between the building blocks and the one-launch search, each
+    against the plain kernel on the device."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(nn.LIB_PATH), "nn_bench")
+    if not os.path.exists(exe):
+        pytest.skip("nn_bench not built")
+    out = subprocess.run([exe, "--sweep", "fuzz"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{"op":')]
+    assert len(rows) == 240 and all(r["mismatch_vs_plain"] == 0 for r in rows), \
+        [(r["k"], r["m"], r["n"], r["quant"], r["op"], r["plan"][:24]) for r in rows if r["mismatch_vs_plain"] != 0]
+
+
 @pytest.mark.parametrize("k", list(range(3, 17)))
 def test_phased_query_register_kernel_layouts(nn, oracle, k):
     """nn_qflex_kernel: 128 threads = query groups x reference phases.  Query counts that give very
