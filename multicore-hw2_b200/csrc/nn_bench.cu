@@ -65,7 +65,7 @@ struct Cfg
 {
     int k = 16, m = 4096;
     long long n = 1 << 20;
-    int variant = 0, q = 0, scalar = 2, splits = 0, waves = 4, iters = 10, warmup = 3, check = 0, soa = 0, repack = 0,
+    int variant = 0, q = 0, scalar = 2, splits = 0, waves = 8, iters = 10, warmup = 3, check = 0, soa = 0, repack = 0,
         rreg_ctas = 0, quant = 0, ldg = 0, fused = 0;
     std::string tag;
 };

@@ -78,6 +78,7 @@ struct Options
     std::atomic<int64_t> stage_threads{-1};  // pageable inputs: host threads staging into pinned buffers (-1 auto, 0 off)
     std::atomic<int64_t> stage_min_bytes{48 << 20}; // pageable reference sets from this size on go through the staging threads
     std::atomic<int64_t> flex_deep_ring{1};  // phased kernel ring: 1 = 4 x ~12 KB (default), 0 = 3 x ~8 KB, -1 = deep only beyond 8 phases
+    std::atomic<int64_t> qgroup{128};        // CTA order of the query-register kernels: query tiles per group (1 = split fastest)
     std::atomic<int64_t> search_group{8};    // host entry: at most this many landed H2D chunks are searched by one launch
     std::atomic<int64_t> stage_one_stream{1}; // staging threads push their copies on the shared copy stream (5% faster than a stream each)
     std::atomic<int64_t> index_graph{1};     // resident index on one GPU: replay a captured CUDA graph for small batches
@@ -126,6 +127,8 @@ extern "C" int nn_b200_set_option(const char *name, int64_t value)
         g_opt.stage_min_bytes = value;
     else if (s == "search_group")
         g_opt.search_group = value;
+    else if (s == "qgroup")
+        g_opt.qgroup = value;
     else if (s == "flex_deep_ring")
         g_opt.flex_deep_ring = value;
     else if (s == "stage_one_stream")
@@ -927,6 +930,7 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
         a.n = (uint32_t)n;
         a.index_base = index_base;
         a.splits = p.splits;
+        a.qgroup = (uint32_t)std::max<int64_t>(1, g_opt.qgroup.load());
         a.refs_per_split = p.refs_per_split;
         a.keys = keys;
         a.neg_zero = -0.0f;
@@ -949,6 +953,7 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
         a.n = (uint32_t)n;
         a.index_base = index_base;
         a.splits = p.splits;
+        a.qgroup = (uint32_t)std::max<int64_t>(1, g_opt.qgroup.load());
         a.refs_per_split = p.refs_per_split;
         a.tile_queries = p.tile_queries;
         a.ng = (uint32_t)p.ng;

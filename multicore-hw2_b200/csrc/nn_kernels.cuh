@@ -91,8 +91,8 @@
 #ifndef NN_QFLEX_UNROLL_Q2
 #define NN_QFLEX_UNROLL_Q2 4
 #endif
-#ifndef NN_QTILE_FASTEST
-#define NN_QTILE_FASTEST 0 // CTA order of the query-register kernels: 1 = query tile fastest (A/B: see nn_qreg_kernel)
+#ifndef NN_CTA_ORDER
+#define NN_CTA_ORDER 2 // CTA index -> (split, query tile): 2 grouped on a 2-D grid (default); A/B: 0 split fastest, 1 grouped, 1-D
 #endif
 #ifndef NN_QREG_REGCAP_LOW
 #define NN_QREG_REGCAP_LOW 0 // 1: always compile the query-register kernel for 4 CTAs/SM (128 regs)
@@ -269,6 +269,25 @@ __device__ __forceinline__ void finish_group(const Finish &f, unsigned long long
             f.keys_out[q_begin + i] = key;
         __stcg(keys + q_begin + i, KEY_INIT);
     }
+}
+
+// CTA index -> (reference split, query tile).  The query tiles are taken in groups of `qgroup`; inside
+// a group the tile index runs fastest, the split next, and the groups follow one another.  qgroup = 1 is
+// "split fastest" (consecutive CTAs = the splits of one tile), qgroup >= #tiles is "tile fastest".
+__device__ __forceinline__ void cta_to_work(uint32_t splits, uint32_t qgroup, uint32_t &split, uint32_t &qtile)
+{
+    if (qgroup <= 1u)
+    {
+        split = blockIdx.x % splits;
+        qtile = blockIdx.x / splits;
+        return;
+    }
+    const uint32_t qtiles = gridDim.x / splits;
+    const uint32_t per_group = qgroup * splits;
+    const uint32_t grp = blockIdx.x / per_group, within = blockIdx.x - grp * per_group;
+    const uint32_t in_grp = min(qgroup, qtiles - grp * qgroup); // the last group may be smaller
+    split = within / in_grp;
+    qtile = grp * qgroup + within % in_grp;
 }
 
 // References come in 16-byte-aligned groups of G points (G*K floats = F4 float4) so that every
@@ -579,19 +598,26 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);
 
     const int tid = threadIdx.x;
-    // CTA order: reference split fastest.  With several waves (BASELINE config 4: 128 query tiles x 37
-    // splits = 8 waves) every wave then re-streams the reference set from HBM: 8.9 GB of DRAM reads for a
-    // 1.07 GB set (ncu r02_cfg4_qreg) -- 6 GB/s on average, 0.1% of the HBM bandwidth of an FP32-bound
-    // kernel.  The other order (query tile fastest: resident CTAs cover ALL tiles of a few splits) cuts
-    // that to 2.4 GB at an L2 hit rate of 96.7% but measured 1.3% SLOWER at configs 4 and 2 and 2% at
-    // k = 8, m = 65536 (128 CTAs in lockstep on the same lines of one L2 slice), so it stays an A/B switch.
-#if NN_QTILE_FASTEST
-    const uint32_t qtiles = gridDim.x / a.splits;
-    const uint32_t qtile = blockIdx.x % qtiles;
-    const uint32_t split = blockIdx.x / qtiles;
-#else
+    // CTA order.  Launch order is x fastest, then y: x = (reference split, query tile within its group),
+    // y = group of a.qgroup query tiles.  The CTAs that are resident together then cover MANY query tiles
+    // of a FEW reference splits, so a split is fetched from HBM once and served to the other tiles by the
+    // L2.  With the splits of one tile consecutive instead (round 1), BASELINE config 4 -- 128 tiles x 37
+    // splits = 8 waves -- re-streamed the set in every wave and read 55 GB from DRAM for a 1.07 GB
+    // reference set (L2 hit rate 46%); grouped by 128 tiles: 1.6 GB (97%).  Same speed either way (the
+    // kernel is FP32-bound) -- but HOW the two indices are computed matters: the same order written as one
+    // division/modulo chain on a 1-D grid (NN_CTA_ORDER=1) ran 1.6% slower at configs 4 and 2 whatever
+    // the group size (1496 vs 1473 ms), a pure code-generation effect on the unrolled loop that follows.
+#if NN_CTA_ORDER == 0 // the original: split fastest, no grouping
     const uint32_t split = blockIdx.x % a.splits;
     const uint32_t qtile = blockIdx.x / a.splits;
+#elif NN_CTA_ORDER == 2 // 2-D grid: x = (split, tile within its group), y = group of a.qgroup tiles
+    const uint32_t split = blockIdx.x / a.qgroup;
+    const uint32_t qtile = blockIdx.y * a.qgroup + blockIdx.x % a.qgroup;
+    if (qtile * (uint32_t)(NT * Q) >= (uint32_t)a.m)
+        return; // (the last group may hold fewer tiles)
+#else
+    uint32_t split, qtile;
+    cta_to_work(a.splits, a.qgroup, split, qtile);
 #endif
     // This CTA's references: [r0, r1).  r0 is a multiple of 8 points (a whole chunk, 16-byte aligned for every
     // k); whole chunks [r0, r1c) stream through the TMA ring in tiles of up to TR points, and the
@@ -932,13 +958,17 @@ __global__ void __launch_bounds__(NT, qflex_minb<K, Q>()) nn_qflex_kernel(const 
 
     const int tid = threadIdx.x;
     // CTA order: see nn_qreg_kernel
-#if NN_QTILE_FASTEST
-    const uint32_t qtiles = gridDim.x / a.splits;
-    const uint32_t qtile = blockIdx.x % qtiles;
-    const uint32_t split = blockIdx.x / qtiles;
-#else
+#if NN_CTA_ORDER == 0 // the original: split fastest, no grouping
     const uint32_t split = blockIdx.x % a.splits;
     const uint32_t qtile = blockIdx.x / a.splits;
+#elif NN_CTA_ORDER == 2 // 2-D grid: x = (split, tile within its group), y = group of a.qgroup tiles
+    const uint32_t split = blockIdx.x / a.qgroup;
+    const uint32_t qtile = blockIdx.y * a.qgroup + blockIdx.x % a.qgroup;
+    if (qtile * a.tile_queries >= (uint32_t)a.m)
+        return; // (the last group may hold fewer tiles)
+#else
+    uint32_t split, qtile;
+    cta_to_work(a.splits, a.qgroup, split, qtile);
 #endif
     const uint32_t ng = a.ng, np = a.np;
     // lanes beyond NG*NP shadow the last phase of group 0 (same addresses: broadcast) and publish nothing

@@ -45,7 +45,14 @@ static cudaError_t launch_qreg_one(const QregArgs &a, uint32_t qtiles, cudaStrea
     });
     if (e != cudaSuccess)
         return e;
+#if NN_CTA_ORDER == 2
+    const uint32_t qg = a.qgroup < 1 ? 1u : (a.qgroup > qtiles ? qtiles : a.qgroup);
+    QregArgs b = a;
+    b.qgroup = qg;
+    kern<<<dim3(qg * a.splits, (qtiles + qg - 1) / qg), NT, QregCfg<K>::SMEM, st>>>(b);
+#else
     kern<<<qtiles * a.splits, NT, QregCfg<K>::SMEM, st>>>(a);
+#endif
     return cudaGetLastError();
 }
 
@@ -145,7 +152,14 @@ static cudaError_t launch_qflex_one(const QflexArgs &a, uint32_t qtiles, cudaStr
     if (a.stages < 2 || a.stages > (uint32_t)kFlexMaxStages || smem > (size_t)kFlexMaxSmem ||
         (size_t)a.stages * a.stage_floats * 4 < (size_t)128 * Q * 8 || (size_t)a.tile_groups * Geo<K>::G * K > a.stage_floats)
         return cudaErrorInvalidValue;
+#if NN_CTA_ORDER == 2
+    const uint32_t qg = a.qgroup < 1 ? 1u : (a.qgroup > qtiles ? qtiles : a.qgroup);
+    QflexArgs b = a;
+    b.qgroup = qg;
+    kern<<<dim3(qg * a.splits, (qtiles + qg - 1) / qg), 128, smem, st>>>(b);
+#else
     kern<<<qtiles * a.splits, 128, smem, st>>>(a);
+#endif
     return cudaGetLastError();
 }
 

@@ -58,6 +58,7 @@ struct QregArgs
     uint32_t n;
     uint32_t index_base;
     uint32_t splits;          // reference splits per query tile
+    uint32_t qgroup = 1;      // CTA order: query tiles per group (cta_to_work, nn_kernels.cuh)
     uint32_t refs_per_split;  // references per split (multiple of 4; the last split takes what is left)
     unsigned long long *keys;
     float neg_zero;           // must be -0.0f: run-time addend of the exact fma(d, d, -0) square
@@ -74,6 +75,7 @@ struct QflexArgs
     uint32_t n;
     uint32_t index_base;
     uint32_t splits;         // reference splits per query tile
+    uint32_t qgroup = 1;     // CTA order: query tiles per group (cta_to_work, nn_kernels.cuh)
     uint32_t refs_per_split; // multiple of np * CH references (the last split takes what is left)
     uint32_t tile_queries;   // queries per query tile, <= ng * Q
     uint32_t ng, np;         // ng * np <= 128

@@ -37,7 +37,7 @@ for wl, cap, kern, alg in [("cfg1", "cfg1_qreg", "nn_qreg_kernel", 65536 * 3 * 4
         continue
     d = raw(p)
     traffic[wl] = {"kernel": kern, "dram_bytes_read": to_bytes(*d["dram__bytes_read.sum"]), "dram_bytes_write": to_bytes(*d["dram__bytes_write.sum"]),
-                   "algorithmic_bytes": alg, "gpu_time_us": float(d["gpu__time_duration.sum"][0].replace(",", "")) * (1e-3 if d["gpu__time_duration.sum"][1] == "ns" else 1.0 if d["gpu__time_duration.sum"][1] == "us" else 1e3),
+                   "algorithmic_bytes": alg, "gpu_time_us": float(d["gpu__time_duration.sum"][0].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}[d["gpu__time_duration.sum"][1]],
                    "source": f"profiles/{tag}_ncu_summary.txt ({tag}_{cap}.ncu-rep, ncu --set full, one launch)"}
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 for name in (f"{tag}_launches_bench_cfg4.csv", f"{tag}_launches_bench_cfg2.csv"):
