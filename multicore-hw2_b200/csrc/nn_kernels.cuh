@@ -1430,6 +1430,9 @@ __global__ void __launch_bounds__(NT, MINB) nn_rreg_kernel(const RregArgs a)
 // slice: 0.407 ms at 16 warps, but 3-4% slower at k = 3 and k = 16), and walking the passes of a
 // many-query launch inside the CTA without draining the ring (grid.y = 1): the extra loop level cost
 // the hot loop 8% at one pass and gained nothing at 13.
+// Round 2: 16 queries per pass (MQ = 16 fits 128 registers with 4-16 bytes of spills): 3-6% faster where
+// the query count is a multiple of 16 (k=8, m=32, n=2^22: 133 -> 127 us), but 3-7% SLOWER with a padded
+// tail (m = 9, 24), at small n (n=2^16: 15.9 -> 20.8 us) and 1% slower at n = 2^26 -- not kept.
 // Tile t of the reference set goes to CTA t % gridDim.x (persistent grid); the ragged end of the set
 // (n % TILE_REFS references) is read with plain loads by the CTA whose turn it is.
 // =============================================================================================
