@@ -48,8 +48,9 @@ extern "C" {
 /* Replaces the global `cudaCallback` (core.h:71, core.cu:1282-1297) and therefore
  * `v8::cudaCallback` (core.cu:856-958) which it forwards to.  Same contract: S and R are host
  * arrays owned by the caller and only read; *results is allocated with malloc(sizeof(int)*m)
- * and freed by the caller (core.cu:935; main.cu:98).  Synchronous.  Uses every visible GPU
- * (at most n, core.cu:867-868; NN_B200_GPUS=<count> caps it), sharding R contiguously
+ * and freed by the caller (core.cu:935; main.cu:98).  Synchronous.  Uses as many of the visible GPUs
+ * as pay for themselves (nn_b200_plan_gpus -- the role of the small-n shortcut core.cu:871-872; at
+ * most n, core.cu:867-868; NN_B200_GPUS=<count> caps it), sharding R contiguously
  * (core.cu:875-883) and merging per-query packed keys on the devices -- every GPU's search kernel
  * folds into GPU 0's key array with 64-bit system-scope atomicMin over NVLink peer memory, or, where
  * peer access is unavailable, one ncclAllReduce(min, u64) -- instead of the reference's host-side
