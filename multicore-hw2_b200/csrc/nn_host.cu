@@ -1688,8 +1688,11 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
     // after everything has been enqueued (open item), and the chunks cost extra launches.
     int64_t want_feeders = g_opt.stage_threads.load();
     if (want_feeders < 0)
+        // up to 8 threads; 4 below 96 MiB, where more threads only contend for the driver (64 MiB = BASELINE
+        // config 2: 6.48 ms with 4, 7.05 ms with 8, 6.24 ms pinned; 256 MiB: 11.1 / 7.3 / 5.2 ms)
         want_feeders = bytesR >= (size_t)g_opt.stage_min_bytes.load()
-                           ? std::max(2u, std::min(8u, std::thread::hardware_concurrency() / (unsigned)std::max(1, g_active_gpus.load())))
+                           ? std::max(2u, std::min(bytesR >= ((size_t)96 << 20) ? 8u : 4u,
+                                                   std::thread::hardware_concurrency() / (unsigned)std::max(1, g_active_gpus.load())))
                            : 0;
     const bool staged = want_feeders > 0 && count > 0 && is_pageable(R);
     int64_t chunk_bytes = g_opt.h2d_chunk_bytes.load();
