@@ -236,3 +236,28 @@ def test_peer_merge_needs_a_gpu_and_checks_its_arguments(nn):
         from multicore_hw2_b200 import sharded
         with pytest.raises(nn.NNError):
             sharded.PeerMerge(10)
+
+
+def test_bench_helpers_on_the_cpu():
+    """bench.py's host-side pieces that need no GPU: both arms name the workload identically (the driver
+    compares the strings), the oracle spot check accepts the oracle's own answer and rejects a corrupted one,
+    and the roofline arithmetic is the north_star definition (3k lane-ops per pair vs n*k*4 bytes)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.workload_string("cfg4", "strong", 1) == bench.workload_string("cfg4", "strong", 8)
+    assert "configs[3]" in bench.workload_string("cfg4", "strong", 8)
+    from oracle import oracle
+    rng = np.random.default_rng(3)
+    S, R = rng.random((40, 5), dtype=np.float32), rng.random((3001, 5), dtype=np.float32)
+    good = oracle.v0(S, R, threads=0)
+    bad = good.copy()
+    bad[-1] = (bad[-1] + 1) % 3001          # the last query is always among the checked rows
+    ok, n = bench.spot_check(5, 40, S, R, {"good": good, "bad": bad})
+    assert n == 16 and ok == {"good": True, "bad": False}
+    peaks = {"hbm_gbs": 6550.0, "sm_max_mhz": 1965.0, "source": "test"}
+    r = bench.roofline_of(16, 4096, 1 << 20, 5.9, peaks, 148, "qreg k=16", "cfgX")
+    assert r["bound"] == "fp32" and abs(r["frac"] - (3 * 16 * 4096 * (1 << 20) / (148 * 128 * 1.965e9)) / 5.9e-3) < 1e-9
+    r = bench.roofline_of(8, 1, 1 << 26, 0.33, peaks, 148, "rreg k=8", "cfgX")
+    assert r["bound"] == "hbm" and abs(r["achieved"] - (1 << 26) * 8 * 4 / 0.33e-3 / 1e9) < 1e-6
