@@ -390,6 +390,26 @@ def test_config4_scaled_and_sharded(nn, oracle):
     _check_subset_against_oracle(nn, oracle, dS, dR, keys, rows)
 
 
+def test_config4_full_size(nn, oracle):
+    """BASELINE config 4 at FULL size (k=16, m=65536, n=2^24; the bench default): the one-launch search
+    against the oracle on 24 queries over all 2^24 references, and against the same set folded as 8 shards
+    with global index bases (what 8 GPUs compute) on all 65536 queries."""
+    import torch
+    from multicore_hw2_b200 import device
+    m, n = 65536, 1 << 24
+    dS, dR = _device_uniform(1004, m, 16), _device_uniform(2004, n, 16)
+    ws = device.Workspace(m)
+    idx = device.search(dS, dR, ws)
+    keys = device.new_keys(m)
+    for p in range(8):
+        b, c = nn.shard_range(n, 8, p)
+        device.nearest_keys(dS, dR[b:b + c], keys, b)
+    assert torch.equal(device.keys_unpack(keys), idx)
+    rows = torch.arange(0, m, 2801, device="cuda")
+    _check_subset_against_oracle(nn, oracle, dS, dR, keys, rows)
+    del dR
+
+
 def test_multi_gpu_host_entry(nn, oracle):
     """v8's job: the host entry shards the references over all visible GPUs and merges the keys --
     by system-scope atomicMin into GPU 0's key array from inside every GPU's search kernel (default)
