@@ -1,20 +1,15 @@
 #!/bin/bash
-# What the driver's scaling run does, for the GPU counts available on this box: bench.py at N = 1, 2, 4[, 8].
+# the driver's scaling command at N GPUs (both arms), final code
+N=${1:-4}
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-G=$(nvidia-smi -L | wc -l)
-for N in 1 2 4 8; do
-  [ $N -le $G ] || continue
-  if [ $N -eq 1 ]; then
-    timeout 900 python bench.py --gpus 1 --steps 5 --no-cpu-baseline > gpurun_out/scale_n1.json 2> gpurun_out/scale_n1.err
-  else
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 > gpurun_out/scale_n$N.json 2> gpurun_out/scale_n$N.err
-  fi
-  python - <<PY
-import json
-for l in open("gpurun_out/scale_n$N.json"):
-    if l.startswith("{"):
-        d=json.loads(l); e=d["e2e"]
-        print("N=%d value %.4e pairs/s  step %.4f ms  kernel %.4f ms  merge %.4f ms  e2e %.3f ms same=%s launches %d" % (d["n_gpus"], d["value"], d["ms_per_step"], d["roofline"]["kernel_ms"], d["merge_ms"], e["ms_per_call"], e["matches_device_resident_result"], d["gpu_launches"]))
+( time timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_final_n$N.json 2> gpurun_out/r02_final_n$N.err ) 2>&1 | grep real
+python - gpurun_out/r02_final_n$N.json <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+e = d["e2e"]
+print("N", d["n_gpus"], "merge", d["config"]["merge"], "ms/step %.3f value %.4e frac %.3f" % (d["ms_per_step"], d["value"], d["roofline"]["frac"]),
+      "| e2e cudaCallback %.1f ms pinned %.1f nccl-merge %.1f index %.1f" % (e["ms_per_call"], e["pinned"]["ms_per_call"], e["pinned_nccl_merge"]["ms_per_call"], e["resident_index"]["ms_per_call"]),
+      "| peer leg", d.get("peer_merge"), "| parity", d["parity_spot_check"], d["parity_detail"], "| launches", d["gpu_launches"], "clocks", d["clocks"])
 PY
-done
+tail -c 200 gpurun_out/r02_final_n$N.err | grep -v "^$" | tail -2
