@@ -74,14 +74,19 @@ for path in sorted(glob.glob(os.path.join(P, "r02_bench_n*_cfg*.json"))):
 base = {"cfg4": b["ms_per_step"]}
 for c in ("cfg1", "cfg2", "cfg3", "cfg5"):
     base[c] = ac[c]["ms_per_step"]
-rowsm = ["| run | GPUs | merge | ms per step | parallel efficiency vs 1 GPU | per-rank kernel ms (min / max) | same steps with the NCCL all-reduce | oracle check |", "|---|---|---|---|---|---|---|---|"]
+rowsm = ["| run | GPUs | merge | ms per step | parallel efficiency vs 1 GPU | per-rank kernel ms (min / max) | the other merge, same steps | oracle check |", "|---|---|---|---|---|---|---|---|"]
 for name, d, n in mg:
     N = d["n_gpus"]
     cfg = name.split("_")[1]
     eff = base[cfg] / (N * d["ms_per_step"])
     km = d["kernel_ms_min_max_over_ranks"]
-    rowsm.append(f"| {cfg} | {N} | {d['config']['merge']} | {d['ms_per_step']:.4f} | {eff:.3f} | {km[0]:.4f} / {km[1]:.4f} | "
-                 f"{n.get('ms_per_step', float('nan')):.4f} (kernel {n.get('kernel_ms', float('nan')):.4f} + all-reduce {n.get('merge_ms', float('nan')):.4f} + unpack) | "
+    if d["config"]["merge"] == "peer":
+        other = (f"NCCL: {n.get('ms_per_step', float('nan')):.4f} (kernel {n.get('kernel_ms', float('nan')):.4f} + all-reduce "
+                 f"{n.get('merge_ms', float('nan')):.4f} + unpack)")
+    else:
+        pl = d.get("peer_merge") or {}
+        other = f"peer: {pl['ms_per_step']:.4f}" if "ms_per_step" in pl else "—"
+    rowsm.append(f"| {cfg} | {N} | {d['config']['merge']} | {d['ms_per_step']:.4f} | {eff:.3f} | {km[0]:.4f} / {km[1]:.4f} | {other} | "
                  f"{d.get('parity_spot_check') if d.get('parity_spot_check') is not None else 'n/a'} |")
 t = t.replace("@MULTI@", "\n".join(rowsm) if mg else "(see the driver's SCALE record)")
 pg = os.path.join(P, "r02_pageable.txt")
