@@ -213,7 +213,9 @@ NN_B200_API const char *nn_b200_last_error(void);
  * "variant" (0 auto, 1 query-register kernel, 2 reference-register kernel, 3 plain kernel, 4 reference-stream kernel,
  * 5 phased query-register kernel),
  * "splits" (0 auto), "h2d_chunk_bytes", "auto_gpus" (1: nn_b200_plan_gpus picks the GPU count of a host call, 0: all visible), "p2p_merge" (multi-GPU host entry: 1 = the search kernels of
- * every GPU fold into GPU 0's key array with system-scope atomics over NVLink, 0 = NCCL all-reduce).
+ * every GPU fold into GPU 0's key array with system-scope atomics over NVLink, 0 = NCCL all-reduce),
+ * "qreg_super" (query-register kernel: chunks per update of the running (best, where) pair; -1 = by k
+ * and split length, 0 = always per chunk).
  * Returns NN_B200_EINVAL for an unknown name. */
 NN_B200_API int nn_b200_set_option(const char *name, int64_t value);
 

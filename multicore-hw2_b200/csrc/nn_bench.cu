@@ -17,6 +17,10 @@
 #include <string>
 #include <vector>
 
+#ifdef NN_QREG_TIMELINE
+extern "C" void nn_b200_debug_timeline(unsigned long long *p); // debug builds of the library only
+#endif
+
 #define CK(call)                                                                                                       \
     do                                                                                                                 \
     {                                                                                                                  \
@@ -66,7 +70,7 @@ struct Cfg
     int k = 16, m = 4096;
     long long n = 1 << 20;
     int variant = 0, q = 0, scalar = 2, splits = 0, waves = 8, iters = 10, warmup = 3, check = 0, soa = 0, repack = 0,
-        rreg_ctas = 0, quant = 0, ldg = 0, fused = 0;
+        rreg_ctas = 0, quant = 0, ldg = 0, fused = 0, timeline = 0;
     std::string tag;
 };
 
@@ -177,6 +181,61 @@ static void run(const Cfg &c)
             ms.push_back(t);
     }
     CK(cudaGetLastError());
+#ifdef NN_QREG_TIMELINE
+    if (c.timeline && c.fused)
+    { // debug build: where does a small query-register search spend its time? (thread 0 of every CTA)
+        const size_t max_ctas = 1u << 16;
+        unsigned long long *dT = nullptr;
+        CK(cudaMalloc(&dT, max_ctas * 16 * 8));
+        nn_b200_debug_timeline(dT);
+        std::vector<unsigned long long> h(max_ctas * 16);
+        for (int rep = 0; rep < 3; ++rep)
+        {
+            CK(cudaMemset(dT, 0, max_ctas * 16 * 8));
+            CK(cudaDeviceSynchronize());
+            NN(nn_b200_search_device(c.k, c.m, c.n, dS, dR, 0, dWs, dOut, nullptr, nullptr));
+            CK(cudaDeviceSynchronize());
+        }
+        CK(cudaMemcpy(h.data(), dT, max_ctas * 16 * 8, cudaMemcpyDeviceToHost));
+        nn_b200_debug_timeline(nullptr);
+        CK(cudaFree(dT));
+        std::vector<size_t> ctas;
+        unsigned long long t0 = ~0ull;
+        for (size_t i = 0; i < max_ctas; ++i)
+            if (h[i * 16] && h[i * 16 + 5])
+            {
+                ctas.push_back(i);
+                t0 = std::min(t0, h[i * 16]);
+            }
+        auto stat = [&](std::vector<double> v, const char *name) {
+            std::sort(v.begin(), v.end());
+            double sum = 0;
+            for (double x : v)
+                sum += x;
+            printf("  %-28s min %8.2f  p10 %8.2f  med %8.2f  p90 %8.2f  max %8.2f  mean %8.2f\n", name, v.front(),
+                   v[v.size() / 10], v[v.size() / 2], v[v.size() * 9 / 10], v.back(), sum / v.size());
+        };
+        printf("timeline k=%d m=%d n=%lld: %zu CTAs stamped (us; global timer relative to the first CTA's entry)\n", c.k,
+               c.m, c.n, ctas.size());
+        const char *names[6] = {"entry", "queries loaded", "first tile landed", "tile loop done", "folded", "finished"};
+        for (int s = 0; s < 6; ++s)
+        {
+            std::vector<double> v;
+            for (size_t i : ctas)
+                v.push_back((double)(h[i * 16 + s] - t0) * 1e-3);
+            stat(v, names[s]);
+        }
+        printf("phase lengths by the SM clock (us at 1.965 GHz):\n");
+        for (int s = 1; s < 6; ++s)
+        {
+            std::vector<double> v;
+            for (size_t i : ctas)
+                v.push_back((double)(long long)(h[i * 16 + 8 + s] - h[i * 16 + 8 + s - 1]) / 1965.0);
+            stat(v, names[s]);
+        }
+        fflush(stdout);
+    }
+#endif
     std::sort(ms.begin(), ms.end());
     const double med = ms[ms.size() / 2], best = ms[0];
     const double pairs = (double)c.m * (double)c.n;
@@ -297,6 +356,8 @@ int main(int argc, char **argv)
         }
         else if (a == "--fused")
             c.fused = atoi(val());
+        else if (a == "--timeline") // debug builds (-DNN_QREG_TIMELINE) only
+            c.timeline = atoi(val());
         else if (a == "--tag")
             c.tag = val();
         else if (a == "--sweep")

@@ -79,6 +79,7 @@ struct Options
     std::atomic<int64_t> stage_min_bytes{48 << 20}; // pageable reference sets from this size on go through the staging threads
     std::atomic<int64_t> flex_deep_ring{1};  // phased kernel ring: 1 = 4 x ~12 KB (default), 0 = 3 x ~8 KB, -1 = deep only beyond 8 phases
     std::atomic<int64_t> qgroup{128};        // CTA order of the query-register kernels: query tiles per group (1 = split fastest)
+    std::atomic<int64_t> qreg_super{-1};     // query-register kernel: chunks per (best, where) update; -1 = by the split's length
     std::atomic<int64_t> search_group{8};    // host entry: at most this many landed H2D chunks are searched by one launch
     std::atomic<int64_t> stage_one_stream{1}; // staging threads push their copies on the shared copy stream (5% faster than a stream each)
     std::atomic<int64_t> index_graph{1};     // resident index on one GPU: replay a captured CUDA graph for small batches
@@ -129,6 +130,8 @@ extern "C" int nn_b200_set_option(const char *name, int64_t value)
         g_opt.search_group = value;
     else if (s == "qgroup")
         g_opt.qgroup = value;
+    else if (s == "qreg_super")
+        g_opt.qreg_super = value;
     else if (s == "flex_deep_ring")
         g_opt.flex_deep_ring = value;
     else if (s == "stage_one_stream")
@@ -142,6 +145,27 @@ extern "C" int nn_b200_set_option(const char *name, int64_t value)
 extern "C" const char *nn_b200_last_error(void) { return t_err.c_str(); }
 extern "C" int64_t nn_b200_launch_count(void) { return g_launches.load(); }
 extern "C" int nn_b200_last_gpus(void) { return g_last_gpus.load(); }
+
+#ifdef NN_QREG_TIMELINE
+// debug builds only (make EXTRA=-DNN_QREG_TIMELINE): device buffer of 8 time stamps per CTA that the
+// query-register kernel fills (nn_bench --timeline); not part of the ABI of include/nn_b200.h
+static unsigned long long *g_timeline = nullptr;
+extern "C" __attribute__((visibility("default"))) void nn_b200_debug_timeline(unsigned long long *p) { g_timeline = p; }
+#endif
+
+// Chunks per (best, where) update of the query-register kernel (its super-chunk form, nn_kernels.cuh): three
+// instructions per query saved on every chunk but the first of a super-chunk, against a winner re-scan of
+// one super-chunk per query and CTA -- so only on long splits, and only for the k where it measured faster.
+// Option qreg_super: -1 this rule, 0 or 1 off, n > 1 forced (for the k the form is built for).
+static uint32_t qreg_super_for(int k, uint32_t refs_per_split)
+{
+    const int64_t sc = g_opt.qreg_super.load();
+    if (qreg_super_chunks(k) == 0 || sc == 0)
+        return 1u;
+    if (sc > 0)
+        return (uint32_t)std::min<int64_t>(sc, 64);
+    return refs_per_split >= kQregSuperMinRefs ? (uint32_t)qreg_super_chunks(k) : 1u;
+}
 
 // ---------------------------------------------------------------------------------------------
 // per-k dispatch
@@ -932,6 +956,7 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
         a.splits = p.splits;
         a.qgroup = (uint32_t)std::max<int64_t>(1, g_opt.qgroup.load());
         a.refs_per_split = p.refs_per_split;
+        a.super_chunks = qreg_super_for(k, p.refs_per_split);
         a.keys = keys;
         a.neg_zero = -0.0f;
         a.peer_keys = peer;
@@ -941,6 +966,9 @@ static int nearest_keys_impl(int k, int m, int64_t n, const float *d_S, const fl
             if (fin_done)
                 *fin_done = true;
         }
+#ifdef NN_QREG_TIMELINE
+        a.timeline = g_timeline;
+#endif
         CU(k_launch_qreg(k, p.q, p.scalar, a, p.qtiles, st));
         g_launches++;
     }
@@ -1068,9 +1096,9 @@ extern "C" int nn_b200_describe_plan(int k, int m, int64_t n, char *buf, size_t 
         return rc;
     if (p.variant == 1)
         snprintf(buf, len,
-                 "qreg k=%d Q=%d %s tile=%dq x %dr regs=%d occ=%d qtiles=%u splits=%u refs/split=%u ctas=%u sms=%d", k,
+                 "qreg k=%d Q=%d %s tile=%dq x %dr regs=%d occ=%d qtiles=%u splits=%u refs/split=%u ctas=%u sms=%d super=%u", k,
                  p.q, p.scalar == 0 ? "scalar" : (p.scalar == 1 ? "f32x2-dims" : "f32x2-pairs"), p.tile_q, p.tile_r, p.regs, p.occ, p.qtiles, p.splits,
-                 p.refs_per_split, p.qtiles * p.splits, di.sms);
+                 p.refs_per_split, p.qtiles * p.splits, di.sms, p.scalar == 2 ? qreg_super_for(k, p.refs_per_split) : 1u);
     else if (p.variant == 5)
         snprintf(buf, len,
                  "qflex k=%d Q=%d groups=%d phases=%d tile=%uq x %ug ring=%ux%uK regs=%d occ=%d qtiles=%u splits=%u refs/split=%u "

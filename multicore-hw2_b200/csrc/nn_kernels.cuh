@@ -271,6 +271,29 @@ __device__ __forceinline__ void finish_group(const Finish &f, unsigned long long
     }
 }
 
+// Debug builds (-DNN_QREG_TIMELINE): thread 0 of every CTA stamps the phases of the query-register
+// kernel with the global nanosecond timer; nn_bench --timeline prints where a small search's time goes.
+#ifdef NN_QREG_TIMELINE
+__device__ __forceinline__ unsigned long long tl_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define NN_TL(a, i)                                                                                         \
+    do                                                                                                      \
+    {                                                                                                       \
+        if ((a).timeline && threadIdx.x == 0)                                                               \
+        {                                                                                                   \
+            unsigned long long *tl_ = (a).timeline + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16;    \
+            tl_[(i)] = tl_now();                                                                            \
+            tl_[8 + (i)] = (unsigned long long)clock64();                                                   \
+        }                                                                                                   \
+    } while (0)
+#else
+#define NN_TL(a, i) ((void)0)
+#endif
+
 // CTA index -> (reference split, query tile).  The query tiles are taken in groups of `qgroup`; inside
 // a group the tile index runs fastest, the split next, and the groups follow one another.  qgroup = 1 is
 // "split fastest" (consecutive CTAs = the splits of one tile), qgroup >= #tiles is "tile fastest".
@@ -487,11 +510,12 @@ struct QregPrefetch
         NN_QREG_PREFETCH && Q <= 4 && (Q * K + 2 * Geo<K>::G * K + (MATH == 2 ? 52 : 36) <= 128);
 };
 
-// One chunk of CH references against the thread's Q queries; cm[] receives the chunk minima.
+// One chunk of CH references against the thread's Q queries; cm[] receives the chunk minima
+// (ACC: is folded with them -- the caller starts it at +INF and reads it after several chunks).
 // PF: `nxt` holds the chunk's first reference group on entry (loaded while the previous chunk was
 // computed) and the first group of the FOLLOWING chunk on exit, so no shared-memory latency sits
 // between two chunks.
-template <int K, int Q, int MATH, bool PF>
+template <int K, int Q, int MATH, bool PF, bool ACC = false>
 __device__ __forceinline__ void qreg_chunk(const float *__restrict__ sm, const float (&q)[Q][K], float (&cm)[Q],
                                            const float2 nz, float4 (&nxt)[Geo<K>::F4])
 {
@@ -560,7 +584,7 @@ __device__ __forceinline__ void qreg_chunk(const float *__restrict__ sm, const f
             {
                 if ((c & 1) == 0)
                     hold[j] = dist[j];
-                else if (c == 1)
+                else if (c == 1 && !ACC)
                     cm[j] = fminf(hold[j], dist[j]);
                 else
                     cm[j] = fminf(fminf(cm[j], hold[j]), dist[j]);
@@ -577,7 +601,10 @@ constexpr int qreg_minb()
     return (NN_QREG_REGCAP_LOW || Q * K + Geo<K>::G * K + (MATH == 2 ? 52 : 36) <= 128) ? 4 : 3;
 }
 
-template <int K, int Q, int NT, int MATH>
+// SUPER: the (best, where) update runs once per super-chunk of a.super_chunks chunks instead of once per
+// chunk (see the tile loop).  Two instantiations rather than a run-time branch: with both loop forms in
+// one kernel ptxas took 160 registers at k = 16, Q = 4 (3 CTAs per SM instead of 4).
+template <int K, int Q, int NT, int MATH, bool SUPER = false>
 __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(const QregArgs a)
 {
     using C = QregCfg<K>;
@@ -598,6 +625,7 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * C::TILE_BYTES);
 
     const int tid = threadIdx.x;
+    NN_TL(a, 0);
     // CTA order.  Launch order is x fastest, then y: x = (reference split, query tile within its group),
     // y = group of a.qgroup query tiles.  The CTAs that are resident together then cover MANY query tiles
     // of a FEW reference splits, so a split is fetched from HBM once and served to the other tiles by the
@@ -700,7 +728,9 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
         bref[j] = NO_REF;
     }
     __syncthreads();
+    NN_TL(a, 1);
 
+    const int sref = SUPER ? (int)max(a.super_chunks, 1u) * CH : CH; // references per (best, where) update
     uint32_t stage = 0, parity = 0;
     for (uint32_t t = 0; t < ntiles; ++t)
     {
@@ -708,6 +738,10 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
         if (tid == 0 && t + STAGES - 1 < ntiles)
             issue(t + STAGES - 1, (stage + STAGES - 1) % STAGES);
         mbar_wait(&full[stage], parity);
+#ifdef NN_QREG_TIMELINE
+        if (t == 0)
+            NN_TL(a, 2);
+#endif
         const float *sm = tiles + (size_t)stage * C::TILE_FLOATS;
         const uint32_t ref0 = r0 + t * TR;
         const int cnt = (int)min((uint32_t)TR, r1c - ref0);
@@ -718,18 +752,49 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
             for (int i = 0; i < Geo<K>::F4; ++i)
                 nxt[i] = reinterpret_cast<const float4 *>(sm)[i];
         }
-#pragma unroll UNR
-        for (int c = 0; c < cnt; c += CH)
+        // The strict-less update of (best, where) costs three instructions per query.  Long splits do it
+        // once per SUPER-CHUNK of `sref` references (a.super_chunks chunks), across which the minimum
+        // simply keeps accumulating.  It matters because the packed FP32 instructions hold the issue port
+        // for two cycles, so EVERY other instruction costs the FMA pipe a cycle (ncu on all kernels of
+        // this file: fma-pipe-active % + other-instructions-issued % = 100): at k = 16, Q = 4 a chunk is
+        // 376 packed + 41 other instructions (94.8% pipe), 12 of them this update.  Short splits keep the
+        // per-chunk update: their winner re-scan (one super-chunk per query) would cost more than it saves.
+        if constexpr (SUPER)
         {
-            float cm[Q];
-            qreg_chunk<K, Q, MATH, PF>(sm + c * K, q, cm, nz, nxt);
+            for (int c0 = 0; c0 < cnt; c0 += sref)
+            {
+                const int c1 = min(cnt, c0 + sref);
+                float cm[Q];
 #pragma unroll
-            for (int j = 0; j < Q; ++j)
-                if (cm[j] < best[j])
-                {
-                    best[j] = cm[j];
-                    bref[j] = ref0 + c;
-                }
+                for (int j = 0; j < Q; ++j)
+                    cm[j] = __int_as_float(0x7f800000);
+#pragma unroll UNR
+                for (int c = c0; c < c1; c += CH)
+                    qreg_chunk<K, Q, MATH, PF, true>(sm + c * K, q, cm, nz, nxt);
+#pragma unroll
+                for (int j = 0; j < Q; ++j)
+                    if (cm[j] < best[j])
+                    {
+                        best[j] = cm[j];
+                        bref[j] = ref0 + c0;
+                    }
+            }
+        }
+        else
+        {
+#pragma unroll UNR
+            for (int c = 0; c < cnt; c += CH)
+            {
+                float cm[Q];
+                qreg_chunk<K, Q, MATH, PF>(sm + c * K, q, cm, nz, nxt);
+#pragma unroll
+                for (int j = 0; j < Q; ++j)
+                    if (cm[j] < best[j])
+                    {
+                        best[j] = cm[j];
+                        bref[j] = ref0 + c;
+                    }
+            }
         }
         if (++stage == STAGES)
         {
@@ -738,6 +803,7 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
         }
     }
 
+    NN_TL(a, 3);
     if (r1c < r1)
     {
         // ragged end of the reference set (1..CH-1 points): plain loads; the chunk is padded with NaN
@@ -773,79 +839,136 @@ __global__ void __launch_bounds__(NT, qreg_minb<K, Q, MATH>()) nn_qreg_kernel(co
         if (bref[j] != NO_REF && qi < a.m)
         {
             uint32_t idx = bref[j];
-            if (in_ring)
+            if constexpr (SUPER)
             {
+                // The winner is the lowest index at distance best[j] inside the super-chunk that first reached
+                // it: [bref, bref + sref), cut at the end of this CTA's range (the window may run into later
+                // chunks of the range -- their references are no closer, and a tie there has a higher index).
+                // Scanned from the top down so that the lowest index is the last one written.
+                const uint32_t wn = min(bref[j] + (uint32_t)sref, r1) - bref[j];
                 constexpr int G = Geo<K>::G, F4 = Geo<K>::F4;
-                const float4 *p4 = reinterpret_cast<const float4 *>(tiles + (size_t)(bref[j] - r0) * K);
-#pragma unroll
-                for (int g0 = CH - G; g0 >= 0; g0 -= G)
+                if (in_ring || (VEC && wn % CH == 0))
                 {
-                    float grp[G * K];
-#pragma unroll
-                    for (int i = 0; i < F4; ++i)
+                    // whole chunks: they start on a 16-byte boundary (chunk starts are multiples of 4 points),
+                    // so they are re-read group by group with 128-bit loads -- from the ring when the CTA's
+                    // whole range is still there, else from global memory (L2)
+                    const float4 *p4 = in_ring ? reinterpret_cast<const float4 *>(tiles + (size_t)(bref[j] - r0) * K)
+                                               : reinterpret_cast<const float4 *>(a.R + (size_t)bref[j] * K);
+                    for (int cc = (int)wn - CH; cc >= 0; cc -= CH)
                     {
-                        const float4 v = p4[(g0 / G) * F4 + i];
-                        grp[4 * i + 0] = v.x;
-                        grp[4 * i + 1] = v.y;
-                        grp[4 * i + 2] = v.z;
-                        grp[4 * i + 3] = v.w;
-                    }
 #pragma unroll
-                    for (int g = G - 1; g >= 0; --g)
-                    {
-                        const float d = sqdist<K, 0, false>(q[j], &grp[g * K]);
-                        if (d == best[j])
-                            idx = bref[j] + g0 + g;
+                        for (int g0 = CH - G; g0 >= 0; g0 -= G)
+                        {
+                            float grp[G * K];
+#pragma unroll
+                            for (int i = 0; i < F4; ++i)
+                            {
+                                const float4 *src = p4 + ((cc + g0) / G) * F4 + i;
+                                const float4 v = in_ring ? *src : __ldg(src);
+                                grp[4 * i + 0] = v.x;
+                                grp[4 * i + 1] = v.y;
+                                grp[4 * i + 2] = v.z;
+                                grp[4 * i + 3] = v.w;
+                            }
+#pragma unroll
+                            for (int g = G - 1; g >= 0; --g)
+                            {
+                                const float d = sqdist<K, 0, false>(q[j], &grp[g * K]);
+                                if (d == best[j])
+                                    idx = bref[j] + cc + g0 + g;
+                            }
+                        }
                     }
                 }
-            }
-            else if (VEC && bref[j] + CH <= a.n)
-            {
-                // whole chunk inside the set: it starts on a 16-byte boundary (chunk starts are
-                // multiples of 4 points), so it is re-read group by group with 128-bit loads -- a
-                // quarter of the load instructions, each of which touches 32 sectors per warp
-                constexpr int G = Geo<K>::G, F4 = Geo<K>::F4;
-                const float4 *p4 = reinterpret_cast<const float4 *>(a.R + (size_t)bref[j] * K);
-#pragma unroll
-                for (int g0 = CH - G; g0 >= 0; g0 -= G)
+                else
                 {
-                    float grp[G * K];
-#pragma unroll
-                    for (int i = 0; i < F4; ++i)
+                    for (int c = (int)wn - 1; c >= 0; --c)
                     {
-                        const float4 v = __ldg(p4 + (g0 / G) * F4 + i);
-                        grp[4 * i + 0] = v.x;
-                        grp[4 * i + 1] = v.y;
-                        grp[4 * i + 2] = v.z;
-                        grp[4 * i + 3] = v.w;
-                    }
-#pragma unroll
-                    for (int g = G - 1; g >= 0; --g)
-                    {
-                        const float d = sqdist<K, 0, false>(q[j], &grp[g * K]);
-                        if (d == best[j])
-                            idx = bref[j] + g0 + g;
-                    }
-                }
-            }
-            else
-            {
-#pragma unroll
-                for (int c = CH - 1; c >= 0; --c)
-                {
-                    const uint32_t r = bref[j] + c;
-                    if (r < a.n)
-                    {
+                        const uint32_t r = bref[j] + c;
                         const float d = sqdist_gmem<K>(q[j], a.R + (size_t)r * K);
                         if (d == best[j])
                             idx = r;
                     }
                 }
             }
+            else
+            {
+                if (in_ring)
+                {
+                    constexpr int G = Geo<K>::G, F4 = Geo<K>::F4;
+                    const float4 *p4 = reinterpret_cast<const float4 *>(tiles + (size_t)(bref[j] - r0) * K);
+#pragma unroll
+                    for (int g0 = CH - G; g0 >= 0; g0 -= G)
+                    {
+                        float grp[G * K];
+#pragma unroll
+                        for (int i = 0; i < F4; ++i)
+                        {
+                            const float4 v = p4[(g0 / G) * F4 + i];
+                            grp[4 * i + 0] = v.x;
+                            grp[4 * i + 1] = v.y;
+                            grp[4 * i + 2] = v.z;
+                            grp[4 * i + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int g = G - 1; g >= 0; --g)
+                        {
+                            const float d = sqdist<K, 0, false>(q[j], &grp[g * K]);
+                            if (d == best[j])
+                                idx = bref[j] + g0 + g;
+                        }
+                    }
+                }
+                else if (VEC && bref[j] + CH <= a.n)
+                {
+                    // whole chunk inside the set: it starts on a 16-byte boundary (chunk starts are
+                    // multiples of 4 points), so it is re-read group by group with 128-bit loads -- a
+                    // quarter of the load instructions, each of which touches 32 sectors per warp
+                    constexpr int G = Geo<K>::G, F4 = Geo<K>::F4;
+                    const float4 *p4 = reinterpret_cast<const float4 *>(a.R + (size_t)bref[j] * K);
+#pragma unroll
+                    for (int g0 = CH - G; g0 >= 0; g0 -= G)
+                    {
+                        float grp[G * K];
+#pragma unroll
+                        for (int i = 0; i < F4; ++i)
+                        {
+                            const float4 v = __ldg(p4 + (g0 / G) * F4 + i);
+                            grp[4 * i + 0] = v.x;
+                            grp[4 * i + 1] = v.y;
+                            grp[4 * i + 2] = v.z;
+                            grp[4 * i + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int g = G - 1; g >= 0; --g)
+                        {
+                            const float d = sqdist<K, 0, false>(q[j], &grp[g * K]);
+                            if (d == best[j])
+                                idx = bref[j] + g0 + g;
+                        }
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int c = CH - 1; c >= 0; --c)
+                    {
+                        const uint32_t r = bref[j] + c;
+                        if (r < a.n)
+                        {
+                            const float d = sqdist_gmem<K>(q[j], a.R + (size_t)r * K);
+                            if (d == best[j])
+                                idx = r;
+                        }
+                    }
+                }
+            }
             fold_key(a.keys + qi, pack_key(best[j], a.index_base + idx), a.peer_keys);
         }
     }
+    NN_TL(a, 4);
     finish_group(a.fin, a.keys, qtile, a.splits, qt_begin, min(NT * Q, a.m - qt_begin));
+    NN_TL(a, 5);
 }
 
 // =============================================================================================

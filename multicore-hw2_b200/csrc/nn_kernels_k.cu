@@ -35,10 +35,15 @@ struct PerDeviceOnce
     }
 };
 
-template <int K, int Q, int NT, int MATH>
+// SUPER: the super-chunk form of the tile loop (a.super_chunks > 1; built for the pair-packed tiles of the
+// k for which it measured faster, qreg_super_chunks(k) > 0)
+template <int K, int Q, int NT, int MATH, bool SUPER = false>
 static cudaError_t launch_qreg_one(const QregArgs &a, uint32_t qtiles, cudaStream_t st)
 {
-    auto kern = nn_qreg_kernel<K, Q, NT, MATH>;
+    if constexpr (!SUPER && MATH == 2 && qreg_super_chunks(K) > 0)
+        if (a.super_chunks > 1u)
+            return launch_qreg_one<K, Q, NT, MATH, true>(a, qtiles, st);
+    auto kern = nn_qreg_kernel<K, Q, NT, MATH, SUPER>;
     static PerDeviceOnce once;
     const cudaError_t e = once([&] {
         return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QregCfg<K>::SMEM);

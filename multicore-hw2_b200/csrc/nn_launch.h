@@ -50,6 +50,16 @@ struct Finish
     PeerSync peer;                          // peer.arrive != nullptr: multi-process mode (results/keys_out: rank 0's)
 };
 
+// Super-chunk form of nn_qreg_kernel (the (best, where) update once per several chunks): chunks per update
+// on long splits, by k; 0 = the form is not built for this k.  From the per-k A/B on B200
+// (profiles/r02_super_chunks.txt: m = 65536, n = 2^21): +2.7% at k = 7, +3.6% at k = 15, +1.4% at k = 14,
+// +0.4..1.1% at k = 4, 5, 6, 11, 16; nothing or a loss at k = 3, 8, 9, 10, 12, 13.
+constexpr int qreg_super_chunks(int k)
+{
+    return (k == 4 || k == 5 || k == 6 || k == 7 || k == 15 || k == 16) ? 16 : ((k == 11 || k == 14) ? 8 : 0);
+}
+constexpr uint32_t kQregSuperMinRefs = 65536; // splits at least this long use it (its winner re-scan is per CTA)
+
 struct QregArgs
 {
     const float *S;
@@ -60,10 +70,14 @@ struct QregArgs
     uint32_t splits;          // reference splits per query tile
     uint32_t qgroup = 1;      // CTA order: query tiles per group (cta_to_work, nn_kernels.cuh)
     uint32_t refs_per_split;  // references per split (multiple of 4; the last split takes what is left)
+    uint32_t super_chunks = 1; // chunks between two (best, where) updates, >= 1 (nn_qreg_kernel: super-chunks)
     unsigned long long *keys;
     float neg_zero;           // must be -0.0f: run-time addend of the exact fma(d, d, -0) square
     int peer_keys;            // keys live in another GPU's memory: fold with system-scope atomics
     Finish fin;               // ticket group = query tile (blockIdx.x / splits), `splits` CTAs each
+#ifdef NN_QREG_TIMELINE
+    unsigned long long *timeline = nullptr; // debug builds: 6 global-timer + 6 SM-clock stamps per CTA, 16 slots (nn_bench --timeline)
+#endif
 };
 
 // Phased query-register kernel (nn_qflex_kernel): 128 threads = ng query groups x np phases.

@@ -172,6 +172,35 @@ def test_wide_query_tiles_on_adversarial_data(nn, oracle, k):
             assert np.array_equal(got, want), (kind, k, q)
 
 
+@pytest.mark.parametrize("k", list(range(3, 17)))
+def test_super_chunk_loop_on_adversarial_data(nn, oracle, k):
+    """The query-register kernel's super-chunk loop form (used on splits of 64K+ references, for the k it
+    is built for): forced with windows of 2, 3 and 8 chunks -- which straddle tiles, the end of a split
+    and the ragged end of the set -- on the tie- and arithmetic-sensitive families, every tile width."""
+    try:
+        nn.set_option("variant", VARIANTS["qreg"])
+        nn.set_option("qreg_super", 3)
+        if "super=3" not in nn.describe_plan(k, 1100, 5003):
+            pytest.skip(f"super-chunk form not built for k={k}")
+        for kind, m, n in (("twins", 300, 2999), ("duplicated", 1100, 5003), ("specials", 300, 1001)):
+            S, R = cases.make(kind, 7200 + k, k, m, n)
+            want = oracle.keys(S, R)
+            for sc in (2, 3, 8):
+                nn.set_option("qreg_super", sc)
+                nn.set_option("splits", 1 if sc == 3 else 0)   # one split: many tiles per CTA, ring re-used
+                for q in (0, 2, 4, 8):
+                    try:
+                        got = gpu_keys(nn, S, R, "qreg", q=q)
+                    except nn.NNError:
+                        assert (q == 8 and k > 8) or (q == 4 and k in (13, 15)), (k, q)
+                        continue
+                    assert np.array_equal(got, want), (kind, k, sc, q)
+    finally:
+        nn.set_option("qreg_super", -1)
+        nn.set_option("splits", 0)
+        nn.set_option("variant", 0)
+
+
 @pytest.mark.parametrize("variant", ["rreg", "rtma"])
 @pytest.mark.parametrize("k,m,n", [(8, 10, 300007), (3, 11, 250001), (16, 12, 120000), (5, 3, 199999), (7, 9, 70001),
                                    (12, 4, 90001), (4, 2, 150001)])
@@ -182,14 +211,17 @@ def test_few_query_tail_passes_across_tiles(nn, oracle, variant, k, m, n):
     assert np.array_equal(gpu_keys(nn, S, R, variant), oracle.keys(S, R))
 
 
-def test_nn_bench_cross_check_sweep(nn):
+@pytest.mark.parametrize("super_chunks", [-1, 3])
+def test_nn_bench_cross_check_sweep(nn, super_chunks):
     """`nn_bench --sweep check`: every k, every kernel family, awkward sizes, 8-level quantised data
-    (ties everywhere), each tuned kernel against the independent plain kernel on the device."""
+    (ties everywhere), each tuned kernel against the independent plain kernel on the device; once more
+    with the query-register kernel's super-chunk loop forced (3 chunks per update)."""
     import subprocess
     exe = os.path.join(os.path.dirname(nn.LIB_PATH), "nn_bench")
     if not os.path.exists(exe):
         pytest.skip("nn_bench not built")
-    out = subprocess.run([exe, "--sweep", "check"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([exe, "--opt", f"qreg_super={super_chunks}", "--sweep", "check"], capture_output=True,
+                         text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{"op":"nearest_keys"')]
     assert len(rows) >= 14 * 6 and all(r["mismatch_vs_plain"] == 0 for r in rows), \
