@@ -1838,9 +1838,23 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
     // launch of a big search has its own wave tail, and config 4's 1 GiB in 4 MiB chunks meant 260
     // launches (e2e 1538 ms for a 1473 ms search; 16 MiB pinned chunks: 1487 ms).
     const size_t group_max = (size_t)std::max<int64_t>(1, std::min<int64_t>(g_opt.search_group.load(), (int64_t)nchunks / 24));
+    // When the search of a reference takes much longer than its copy (many queries), the copies run far
+    // ahead of the searches: a launch then takes every chunk that must have landed by the time it starts --
+    // `ahead` references copied per reference searched, from the FP32 bound of the search and a pessimistic
+    // 8 GB/s of copy, halved -- instead of a fixed few.  Config 4 (64 chunks): 34 launches -> 6, each long
+    // enough for the query-register kernel's super-chunk form.
+    const double ahead = g_opt.search_group.load() > 1
+                             ? 0.5 * (3.0 * k * (double)m / (0.9 * 37.2e12)) / ((double)k * sizeof(float) / 8e9)
+                             : 0.0;
     for (size_t ci = 0; ci < nchunks;)
     {
-        const size_t ce = std::min(nchunks, ci + (ci < 4 ? (size_t)1 : group_max));
+        size_t ce = std::min(nchunks, ci + (ci < 4 ? (size_t)1 : group_max));
+        if (ci >= 4 && ahead >= 4.0)
+        {
+            const double landed = (double)chunks[ci].first * ahead; // references searched so far x ahead
+            while (ce < nchunks && (double)(chunks[ce].first + chunks[ce].second) <= landed)
+                ++ce;
+        }
         const int64_t off = chunks[ci].first;
         int64_t cnt = 0;
         for (size_t cj = ci; cj < ce; ++cj)

@@ -9,13 +9,15 @@ import csv, json, os, shutil, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
-caps = ["cfg1_qreg", "cfg2_qreg", "cfg3_rtma", "cfg4_qreg", "cfg5_qreg", "cfg4s_qreg", "cfg5s_qreg", "m100k8_qflex", "m100k3_qflex",
+caps = ["cfg1_qreg", "cfg2_qreg", "cfg3_rtma", "cfg4_qreg", "cfg4q_qreg_super", "cfg5_qreg", "cfg4s_qreg", "cfg5s_qreg", "m100k8_qflex", "m100k3_qflex",
         "cfg3shard_rtma", "m1_rreg", "repack_k16"]
 paths = [os.path.join(ROOT, "gpurun_out", f"{tag}_{c}.raw.csv") for c in caps]
 paths = [p for p in paths if os.path.exists(p)]
 out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py")] + paths, capture_output=True, text=True).stdout
 hdr = (f"# ncu --set full --clock-control none captures ({tag}), one launch each, nn_bench command lines in scripts/gpu_profile.sh\n"
-       "# all five BASELINE configs at FULL size, through the one-launch search (nn_b200_search_device); m100* = 100 queries x 2^22 references (phased kernel)\n")
+       "# all five BASELINE configs at FULL size, through the one-launch search (nn_b200_search_device); m100* = 100 queries x 2^22 references (phased kernel)\n"
+       "# cfg4q_qreg_super = config 4 at a quarter of its references (k=16, m=65536, n=2^22) with the super-chunk loop form that config 4 now runs;\n"
+       "#   cfg4_qreg is the earlier full-size capture of the per-chunk form (same tiles, grid order and DRAM traffic)\n")
 open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.txt"), "w").write(hdr + out)
 print(out)
 
