@@ -1836,13 +1836,13 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
     // Copy granularity and search granularity are decoupled: the copies stay small (early start, double
     // buffers), but once the pipeline runs several landed chunks are searched by ONE launch -- every
     // launch of a big search has its own wave tail, and config 4's 1 GiB in 4 MiB chunks meant 260
-    // launches (e2e 1538 ms for a 1473 ms search; 16 MiB pinned chunks: 1487 ms).
+    // launches (e2e 1538 ms for a 1473 ms search; 16 MiB pinned chunks: 1487 ms; a fixed 2 chunks per launch: 1476).
     const size_t group_max = (size_t)std::max<int64_t>(1, std::min<int64_t>(g_opt.search_group.load(), (int64_t)nchunks / 24));
     // When the search of a reference takes much longer than its copy (many queries), the copies run far
     // ahead of the searches: a launch then takes every chunk that must have landed by the time it starts --
     // `ahead` references copied per reference searched, from the FP32 bound of the search and a pessimistic
     // 8 GB/s of copy, halved -- instead of a fixed few.  Config 4 (64 chunks): 34 launches -> 6, each long
-    // enough for the query-register kernel's super-chunk form.
+    // enough for the query-register kernel's super-chunk form (e2e 1476.5 -> 1466.6 ms for a 1463.7 ms search).
     const double ahead = g_opt.search_group.load() > 1
                              ? 0.5 * (3.0 * k * (double)m / (0.9 * 37.2e12)) / ((double)k * sizeof(float) / 8e9)
                              : 0.0;
