@@ -15,7 +15,7 @@ Everything computes in ``libnn_b200.so`` (hand-written sm_100a CUDA behind the C
 include/nn_b200.h).  There is no CPU fallback."""
 from ._lib import KEY_INIT, LIB_PATH, NNError, build, lib  # noqa: F401
 from .api import (Index, cudaCallback, describe_plan, device_count, last_gpus, launch_count, plan_gpus,  # noqa: F401
-                  probe_fp32, search_host, set_option, shard_range)
+                  plan_search_groups, probe_fp32, search_host, set_option, shard_range)
 
-__all__ = ["cudaCallback", "search_host", "Index", "describe_plan", "device_count", "launch_count", "plan_gpus", "last_gpus", "set_option",
+__all__ = ["cudaCallback", "search_host", "Index", "describe_plan", "device_count", "launch_count", "plan_gpus", "plan_search_groups", "last_gpus", "set_option",
            "shard_range", "probe_fp32", "KEY_INIT", "LIB_PATH", "NNError", "build", "lib"]

@@ -1356,6 +1356,60 @@ static int plan_gpus(int k, int m, int64_t n, int visible, bool pinned)
     return (int)cap;
 }
 
+// Search launches over one shard's H2D chunk list (pure arithmetic): ends[g] = one past the last chunk of
+// launch g.  The copies stay small (early start, double buffers), but once the pipeline runs several chunks
+// are searched by ONE launch -- every launch of a big search has its own wave tail, and config 4's 1 GiB in
+// 4 MiB chunks meant 260 launches (e2e 1538 ms for a 1473 ms search; 16 MiB pinned chunks: 1487 ms; a fixed
+// 2 chunks per launch: 1476 ms).  The first four chunks go one by one; then
+//  * a fixed few (`search_group`, at most 1/24 of the list) when the copy is the slower side, so that the
+//    search of the last group, which nothing overlaps, stays short;
+//  * when the search of a reference takes much longer than its copy (many queries) the copies run far
+//    ahead of the searches, and a launch takes every chunk that must have landed by the time it starts:
+//    `ahead` references copied per reference searched, from the FP32 bound of the search and a pessimistic
+//    8 GB/s of copy, halved.  Config 4 (64 chunks): 34 launches -> 6, each long enough for the
+//    query-register kernel's super-chunk form (e2e 1476.5 -> 1466.6 ms for a 1463.7 ms search).
+static std::vector<size_t> plan_search_groups(int k, int m, const std::vector<std::pair<int64_t, int64_t>> &chunks,
+                                              int64_t search_group)
+{
+    const size_t nchunks = chunks.size();
+    const size_t group_max = (size_t)std::max<int64_t>(1, std::min<int64_t>(search_group, (int64_t)nchunks / 24));
+    const double ahead =
+        search_group > 1 ? 0.5 * (3.0 * k * (double)m / (0.9 * 37.2e12)) / ((double)k * sizeof(float) / 8e9) : 0.0;
+    std::vector<size_t> ends;
+    for (size_t ci = 0; ci < nchunks;)
+    {
+        size_t ce = std::min(nchunks, ci + (ci < 4 ? (size_t)1 : group_max));
+        if (ci >= 4 && ahead >= 4.0)
+        {
+            const double landed = (double)chunks[ci].first * ahead; // references searched so far x ahead
+            while (ce < nchunks && (double)(chunks[ce].first + chunks[ce].second) <= landed)
+                ++ce;
+        }
+        ends.push_back(ce);
+        ci = ce;
+    }
+    return ends;
+}
+
+extern "C" int nn_b200_plan_search_groups(int k, int m, const int64_t *chunk_refs, int nchunks, int *group_ends)
+{
+    if (k < 3 || k > 16 || m < 0 || nchunks < 0 || (nchunks > 0 && (!chunk_refs || !group_ends)))
+        return fail(NN_B200_EINVAL, "bad arguments to nn_b200_plan_search_groups");
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    int64_t off = 0;
+    for (int i = 0; i < nchunks; ++i)
+    {
+        if (chunk_refs[i] <= 0)
+            return fail(NN_B200_EINVAL, "chunk %d holds %lld references", i, (long long)chunk_refs[i]);
+        chunks.emplace_back(off, chunk_refs[i]);
+        off += chunk_refs[i];
+    }
+    const std::vector<size_t> ends = plan_search_groups(k, m, chunks, g_opt.search_group.load());
+    for (size_t g = 0; g < ends.size(); ++g)
+        group_ends[g] = (int)ends[g];
+    return (int)ends.size();
+}
+
 extern "C" int nn_b200_plan_gpus(int k, int m, int64_t n, int visible)
 {
     if (check_shape_quiet(k, m, n) || visible < 0)
@@ -1833,28 +1887,12 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
             });
     }
 
-    // Copy granularity and search granularity are decoupled: the copies stay small (early start, double
-    // buffers), but once the pipeline runs several landed chunks are searched by ONE launch -- every
-    // launch of a big search has its own wave tail, and config 4's 1 GiB in 4 MiB chunks meant 260
-    // launches (e2e 1538 ms for a 1473 ms search; 16 MiB pinned chunks: 1487 ms; a fixed 2 chunks per launch: 1476).
-    const size_t group_max = (size_t)std::max<int64_t>(1, std::min<int64_t>(g_opt.search_group.load(), (int64_t)nchunks / 24));
-    // When the search of a reference takes much longer than its copy (many queries), the copies run far
-    // ahead of the searches: a launch then takes every chunk that must have landed by the time it starts --
-    // `ahead` references copied per reference searched, from the FP32 bound of the search and a pessimistic
-    // 8 GB/s of copy, halved -- instead of a fixed few.  Config 4 (64 chunks): 34 launches -> 6, each long
-    // enough for the query-register kernel's super-chunk form (e2e 1476.5 -> 1466.6 ms for a 1463.7 ms search).
-    const double ahead = g_opt.search_group.load() > 1
-                             ? 0.5 * (3.0 * k * (double)m / (0.9 * 37.2e12)) / ((double)k * sizeof(float) / 8e9)
-                             : 0.0;
+    // Copy granularity and search granularity are decoupled (plan_search_groups).
+    const std::vector<size_t> group_ends = plan_search_groups(k, m, chunks, g_opt.search_group.load());
+    size_t gi = 0;
     for (size_t ci = 0; ci < nchunks;)
     {
-        size_t ce = std::min(nchunks, ci + (ci < 4 ? (size_t)1 : group_max));
-        if (ci >= 4 && ahead >= 4.0)
-        {
-            const double landed = (double)chunks[ci].first * ahead; // references searched so far x ahead
-            while (ce < nchunks && (double)(chunks[ce].first + chunks[ce].second) <= landed)
-                ++ce;
-        }
+        const size_t ce = group_ends[gi++];
         const int64_t off = chunks[ci].first;
         int64_t cnt = 0;
         for (size_t cj = ci; cj < ce; ++cj)

@@ -221,6 +221,39 @@ def test_gpu_count_planner(nn):
         last = g
 
 
+def test_search_launches_over_the_h2d_chunks(nn):
+    """nn_b200_plan_search_groups (pure arithmetic): how the host entry groups the H2D chunks of a shard
+    into search launches.  Every chunk is searched exactly once, in order; the first four chunks go one
+    by one (early start); a copy-bound search keeps small fixed groups (at most 1/24 of the list, so the
+    un-overlapped last launch stays short); a compute-bound one takes what must have landed, never a chunk
+    beyond the pessimistic copy-ahead estimate."""
+    G = nn.plan_search_groups
+    ramp = [32768, 65536, 131072]                       # the pinned path's ramp up to 16 MiB chunks at k = 16
+    cfg4 = ramp + [262144] * 63 + [16777216 - sum(ramp) - 63 * 262144]
+    assert sum(cfg4) == 1 << 24
+    ends = G(16, 65536, cfg4)
+    assert ends[-1] == len(cfg4) and ends == sorted(set(ends)) and ends[:4] == [1, 2, 3, 4]
+    assert len(ends) <= 8                                                   # was 34 launches with 2 chunks each
+    ahead = 0.5 * (3.0 * 16 * 65536 / (0.9 * 37.2e12)) / (16 * 4 / 8e9)
+    starts = [0] + ends[:-1]
+    for b, e in zip(starts, ends):
+        if b >= 4 and e - b > 2:
+            assert sum(cfg4[:e]) <= sum(cfg4[:b]) * ahead                   # only chunks that must have landed
+    # copy-bound (few queries): fixed groups, many launches, each at most 1/24 of the list
+    cfg3 = [65536] * 4 + [524288] * 127
+    ends3 = G(8, 8, cfg3)
+    assert ends3[-1] == len(cfg3) and ends3[:4] == [1, 2, 3, 4]
+    assert max(e - b for b, e in zip([0] + ends3[:-1], ends3)) <= max(1, len(cfg3) // 24)
+    # mid-size (config 2: 4096 queries do not outrun the copy): fixed groups too
+    assert G(16, 4096, [65536] * 16) == list(range(1, 17))
+    # one chunk, no chunk, bad arguments
+    assert G(3, 1024, [65536]) == [1] and G(3, 1024, []) == []
+    with pytest.raises(nn.NNError):
+        G(2, 1, [4096])
+    with pytest.raises(nn.NNError):
+        G(3, 1, [4096, 0])
+
+
 def test_peer_merge_needs_a_gpu_and_checks_its_arguments(nn):
     """nn_b200_peer_*: argument validation works everywhere; without a CUDA device creation fails loudly
     (there is no host-memory stand-in for the NVLink merge)."""
