@@ -23,7 +23,8 @@ One "step" = one complete search with inputs resident in HBM:
 `e2e`     : the same metric through the reference-facing entry point `cudaCallback` with malloc'ed
             (pageable) HOST arrays, exactly what the reference's harness passes and times
             (main.cu:69-73, generator.h:37/44): H2D + search + merge + D2H + malloc inside the timed
-            region, rank 0 driving all N GPUs in one process as v8 does.  `e2e.pinned` is the same call
+            region, rank 0 driving all N GPUs in one process as v8 does; wall clock per call, the MEDIAN
+            of the timed calls (`e2e.ms_spread` holds min / median / mean / max).  `e2e.pinned` is the same call
             (error-code variant) with pinned buffers, `e2e.resident_index` the build-once/query-many API.
 `roofline`: the fused search kernel against the SLOWER of the two bounds north_star names -- 3k FP32
             lane-ops per pair at SMs*128*max clock and n*k*4 reference bytes at the measured HBM copy
