@@ -71,12 +71,16 @@ for path in sorted(glob.glob(os.path.join(P, "r02_bench_n*_cfg*.json"))):
     name = os.path.basename(path).replace("r02_bench_", "").replace(".json", "")
     n = d.get("nccl_merge") or {}
     mg.append((name, d, n))
-base = {"cfg4": b["ms_per_step"]}
+# The multi-GPU lines were measured before the super-chunk loop form took 0.5 % off config 4's 1-GPU step
+# (1473.4 -> 1464.9 ms); their parallel efficiency is quoted against the 1-GPU step of THEIR code state.
+base = {"cfg4": 1473.4}
 for c in ("cfg1", "cfg2", "cfg3", "cfg5"):
     base[c] = ac[c]["ms_per_step"]
 rowsm = ["| run | GPUs | merge | ms per step | parallel efficiency vs 1 GPU | per-rank kernel ms (min / max) | the other merge, same steps | oracle check |", "|---|---|---|---|---|---|---|---|"]
 for name, d, n in mg:
     N = d["n_gpus"]
+    if N == 1:
+        continue
     cfg = name.split("_")[1]
     eff = base[cfg] / (N * d["ms_per_step"])
     km = d["kernel_ms_min_max_over_ranks"]
