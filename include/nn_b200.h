@@ -195,12 +195,13 @@ NN_B200_API int nn_b200_device_count(int64_t n);
  * merge, so small calls stay on one GPU.  `visible` = GPUs available (nn_b200_device_count). */
 NN_B200_API int nn_b200_plan_gpus(int k, int m, int64_t n, int visible);
 /* Introspection of the host entry's ingest pipeline (pure arithmetic, no device needed): the reference
- * set of a shard reaches the GPU in `nchunks` H2D chunks of chunk_refs[i] references; the searches
- * over them are launched in groups of consecutive chunks.  Writes, for every launch g, the index one
+ * set of a shard reaches the GPU in `nchunks` H2D chunks of chunk_refs[i] references (`gpus` GPUs of the
+ * call share the host's copy bandwidth); the searches over them are launched in groups of consecutive chunks.  Writes, for every launch g, the index one
  * past its last chunk into group_ends[g] (room for nchunks entries) and returns the number of
  * launches.  When the search is the slower side (many queries) a launch takes every chunk that must
  * have landed by the time it starts; otherwise a fixed few (option "search_group"). */
-NN_B200_API int nn_b200_plan_search_groups(int k, int m, const int64_t *chunk_refs, int nchunks, int *group_ends);
+NN_B200_API int nn_b200_plan_search_groups(int k, int m, int gpus, const int64_t *chunk_refs, int nchunks,
+                                           int *group_ends);
 
 /* GPUs the most recent nn_b200_cudaCallback / nn_b200_search_host call of this process used. */
 NN_B200_API int nn_b200_last_gpus(void);

@@ -49,8 +49,8 @@ SIGNATURES = {
     "nn_b200_device_count": (ctypes.c_int, [ctypes.c_int64]),
     "nn_b200_launch_count": (ctypes.c_int64, []),
     "nn_b200_plan_gpus": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int]),
-    "nn_b200_plan_search_groups": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
-                                                  ctypes.c_void_p]),
+    "nn_b200_plan_search_groups": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                  ctypes.c_int, ctypes.c_void_p]),
     "nn_b200_last_gpus": (ctypes.c_int, []),
     "nn_b200_last_error": (ctypes.c_char_p, []),
     "nn_b200_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),

@@ -105,12 +105,12 @@ def plan_gpus(k: int, m: int, n: int, visible: int) -> int:
     return lib().nn_b200_plan_gpus(k, m, n, visible)
 
 
-def plan_search_groups(k: int, m: int, chunk_refs) -> list:
-    """Host entry, ingest pipeline (pure arithmetic): for H2D chunks of `chunk_refs` references each, the
-    index one past the last chunk of every search launch."""
+def plan_search_groups(k: int, m: int, chunk_refs, gpus: int = 1) -> list:
+    """Host entry, ingest pipeline (pure arithmetic): for H2D chunks of `chunk_refs` references each (one
+    shard of a call that drives `gpus` GPUs), the index one past the last chunk of every search launch."""
     refs = np.ascontiguousarray(chunk_refs, dtype=np.int64)
     ends = np.zeros(max(len(refs), 1), dtype=np.int32)
-    n = lib().nn_b200_plan_search_groups(k, m, refs.ctypes.data, len(refs), ends.ctypes.data)
+    n = lib().nn_b200_plan_search_groups(k, m, gpus, refs.ctypes.data, len(refs), ends.ctypes.data)
     if n < 0:
         check(n)
     return ends[:n].tolist()

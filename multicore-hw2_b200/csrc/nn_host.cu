@@ -1366,15 +1366,17 @@ static int plan_gpus(int k, int m, int64_t n, int visible, bool pinned)
 //  * when the search of a reference takes much longer than its copy (many queries) the copies run far
 //    ahead of the searches, and a launch takes every chunk that must have landed by the time it starts:
 //    `ahead` references copied per reference searched, from the FP32 bound of the search and a pessimistic
-//    8 GB/s of copy, halved.  Config 4 (64 chunks): 34 launches -> 6, each long enough for the
-//    query-register kernel's super-chunk form (e2e 1476.5 -> 1466.6 ms for a 1463.7 ms search).
+//    8 GB/s of copy shared by the `gpus` GPUs of the call, halved.  Config 4 on one GPU (64 chunks):
+//    34 launches -> 7, each long enough for the query-register kernel's super-chunk form (e2e 1476.5 ->
+//    1464-1467 ms for a 1463-1464 ms search); on 8 GPUs the shards keep the fixed groups.
 static std::vector<size_t> plan_search_groups(int k, int m, const std::vector<std::pair<int64_t, int64_t>> &chunks,
-                                              int64_t search_group)
+                                              int64_t search_group, int gpus)
 {
     const size_t nchunks = chunks.size();
     const size_t group_max = (size_t)std::max<int64_t>(1, std::min<int64_t>(search_group, (int64_t)nchunks / 24));
+    const double copy_rate = 8e9 / (double)std::max(1, gpus); // bytes/s per GPU
     const double ahead =
-        search_group > 1 ? 0.5 * (3.0 * k * (double)m / (0.9 * 37.2e12)) / ((double)k * sizeof(float) / 8e9) : 0.0;
+        search_group > 1 ? 0.5 * (3.0 * k * (double)m / (0.9 * 37.2e12)) / ((double)k * sizeof(float) / copy_rate) : 0.0;
     std::vector<size_t> ends;
     for (size_t ci = 0; ci < nchunks;)
     {
@@ -1391,9 +1393,9 @@ static std::vector<size_t> plan_search_groups(int k, int m, const std::vector<st
     return ends;
 }
 
-extern "C" int nn_b200_plan_search_groups(int k, int m, const int64_t *chunk_refs, int nchunks, int *group_ends)
+extern "C" int nn_b200_plan_search_groups(int k, int m, int gpus, const int64_t *chunk_refs, int nchunks, int *group_ends)
 {
-    if (k < 3 || k > 16 || m < 0 || nchunks < 0 || (nchunks > 0 && (!chunk_refs || !group_ends)))
+    if (k < 3 || k > 16 || m < 0 || gpus < 1 || nchunks < 0 || (nchunks > 0 && (!chunk_refs || !group_ends)))
         return fail(NN_B200_EINVAL, "bad arguments to nn_b200_plan_search_groups");
     std::vector<std::pair<int64_t, int64_t>> chunks;
     int64_t off = 0;
@@ -1404,7 +1406,7 @@ extern "C" int nn_b200_plan_search_groups(int k, int m, const int64_t *chunk_ref
         chunks.emplace_back(off, chunk_refs[i]);
         off += chunk_refs[i];
     }
-    const std::vector<size_t> ends = plan_search_groups(k, m, chunks, g_opt.search_group.load());
+    const std::vector<size_t> ends = plan_search_groups(k, m, chunks, g_opt.search_group.load(), gpus);
     for (size_t g = 0; g < ends.size(); ++g)
         group_ends[g] = (int)ends[g];
     return (int)ends.size();
@@ -1888,7 +1890,7 @@ int enqueue_device(DevCtx &c, int dev, int k, int m, const float *S, const float
     }
 
     // Copy granularity and search granularity are decoupled (plan_search_groups).
-    const std::vector<size_t> group_ends = plan_search_groups(k, m, chunks, g_opt.search_group.load());
+    const std::vector<size_t> group_ends = plan_search_groups(k, m, chunks, g_opt.search_group.load(), g_active_gpus.load());
     size_t gi = 0;
     for (size_t ci = 0; ci < nchunks;)
     {

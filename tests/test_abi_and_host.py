@@ -239,6 +239,10 @@ def test_search_launches_over_the_h2d_chunks(nn):
     for b, e in zip(starts, ends):
         if b >= 4 and e - b > 2:
             assert sum(cfg4[:e]) <= sum(cfg4[:b]) * ahead                   # only chunks that must have landed
+    # the same shard as one of eight GPUs' (the host's copy bandwidth is shared): fixed groups again
+    shard = [16384, 32768] + [65536] * 31
+    e8 = G(16, 65536, shard, gpus=8)
+    assert e8 == list(range(1, len(shard) + 1)) and len(G(16, 65536, shard, gpus=1)) < len(e8)
     # copy-bound (few queries): fixed groups, many launches, each at most 1/24 of the list
     cfg3 = [65536] * 4 + [524288] * 127
     ends3 = G(8, 8, cfg3)
@@ -252,6 +256,8 @@ def test_search_launches_over_the_h2d_chunks(nn):
         G(2, 1, [4096])
     with pytest.raises(nn.NNError):
         G(3, 1, [4096, 0])
+    with pytest.raises(nn.NNError):
+        G(3, 1, [4096], gpus=0)
 
 
 def test_peer_merge_needs_a_gpu_and_checks_its_arguments(nn):
